@@ -1,0 +1,293 @@
+// Flash-attention forward for sm_100a: bf16, head_dim 128, non-causal, ragged tails.
+//   S = Q K^T   : tcgen05.mma SS (Q, K in 128B-swizzled smem via TMA), fp32 S in TMEM
+//   P = softmax : 2 x 128 softmax threads (one row each) read S from TMEM, write bf16 P back over S
+//   O += P V    : tcgen05.mma TS (A = P from TMEM, B = V as an MN-major smem operand), fp32 O in TMEM
+// One CTA = one head x 256 queries (two 128-row Q tiles that ping-pong: while the tensor core works on
+// tile A's MMAs the softmax warps of tile B run, as in FlashAttention-4).  O is rescaled lazily: the
+// running max used for exp2 only moves when the true max grew by more than 8 (log2 units), which is
+// exact because the row sum is kept relative to the same stale max.
+// Warps: 0-3 softmax of Q tile 0, 4-7 softmax of Q tile 1, 8 TMA producer, 9 MMA issuer.
+// TMEM: S0 [0,128) S1 [128,256) O0 [256,384) O1 [384,512); P_i aliases the first 64 columns of S_i.
+// Roofline: tensor pipe, 4*Lq*Lk*128 flops per head.
+#include <math.h>
+
+#include "common.cuh"
+
+namespace prfl {
+
+constexpr int ATT_THREADS = 320;
+constexpr int QT = 128;       // rows per Q tile
+constexpr int KT = 128;       // keys per KV tile
+constexpr int HD = 128;
+constexpr int TILE_BYTES = 128 * 128 * 2;  // 32 KB: any 128 x 128 bf16 tile (two 64-wide TMA boxes)
+constexpr int KV_STAGES = 2;
+constexpr int ATT_SMEM = 2 * TILE_BYTES + 2 * KV_STAGES * TILE_BYTES + 256 + 1024;
+
+struct AttnFwdParams {
+  __nv_bfloat16* o;
+  int64_t o_ld_tok, o_ld_head;
+  float* lse;
+  int Lq, Lk;
+  float scale_log2;
+};
+
+__global__ void __launch_bounds__(ATT_THREADS, 1)
+attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                const __grid_constant__ CUtensorMap tmV, const AttnFwdParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint8_t* sQ = smem;                                  // [2][32 KB]
+  uint8_t* sK = smem + 2 * TILE_BYTES;                 // [KV_STAGES][32 KB]
+  uint8_t* sV = sK + KV_STAGES * TILE_BYTES;           // [KV_STAGES][32 KB]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sV + KV_STAGES * TILE_BYTES);
+  uint64_t* qfull = bars;          // [1]
+  uint64_t* kfull = bars + 1;      // [2]
+  uint64_t* kempty = bars + 3;     // [2]
+  uint64_t* vfull = bars + 5;      // [2]
+  uint64_t* vempty = bars + 7;     // [2]
+  uint64_t* sfull = bars + 9;      // [2]  S_i written by the tensor core
+  uint64_t* pfull = bars + 11;     // [2]  P_i written by the softmax warps
+  uint64_t* ofull = bars + 13;     // [1]  all MMAs retired
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 14);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int head = blockIdx.y;
+  const int q0 = blockIdx.x * (2 * QT);
+  const int n_kv = (p.Lk + KT - 1) / KT;
+
+  if (warp == 8 && lane == 0) {
+    tma_prefetch_desc(&tmQ);
+    tma_prefetch_desc(&tmK);
+    tma_prefetch_desc(&tmV);
+    mbar_init(qfull, 1);
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&kfull[s], 1);
+      mbar_init(&kempty[s], 1);
+      mbar_init(&vfull[s], 1);
+      mbar_init(&vempty[s], 1);
+      mbar_init(&sfull[s], 1);
+      mbar_init(&pfull[s], 4);
+    }
+    mbar_init(ofull, 1);
+    fence_barrier_init();
+  }
+  if (warp == 9) tmem_alloc<512>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 8) {
+    // ------------------------------- TMA producer -------------------------------
+    if (lane == 0) {
+      mbar_arrive_expect_tx(qfull, 2 * TILE_BYTES);
+#pragma unroll
+      for (int t = 0; t < 2; ++t)
+#pragma unroll
+        for (int c = 0; c < 2; ++c) tma_load_3d(sQ + t * TILE_BYTES + c * 16384, &tmQ, qfull, c * 64, q0 + t * QT, head);
+      for (int j = 0; j < n_kv; ++j) {
+        const int s = j % KV_STAGES;
+        const uint32_t ph = (j / KV_STAGES) & 1;
+        mbar_wait(&kempty[s], ph ^ 1);
+        mbar_arrive_expect_tx(&kfull[s], TILE_BYTES);
+#pragma unroll
+        for (int c = 0; c < 2; ++c) tma_load_3d(sK + s * TILE_BYTES + c * 16384, &tmK, &kfull[s], c * 64, j * KT, head);
+        mbar_wait(&vempty[s], ph ^ 1);
+        mbar_arrive_expect_tx(&vfull[s], TILE_BYTES);
+#pragma unroll
+        for (int c = 0; c < 2; ++c) tma_load_3d(sV + s * TILE_BYTES + c * 16384, &tmV, &vfull[s], c * 64, j * KT, head);
+      }
+    }
+  } else if (warp == 9) {
+    // ------------------------------- MMA issuer -------------------------------
+    if (lane == 0) {
+      constexpr uint32_t idesc_qk = make_idesc_bf16(128, 128, 0, 0);
+      constexpr uint32_t idesc_pv = make_idesc_bf16(128, 128, 0, 1);  // A = P (TMEM, K-major), B = V (MN-major)
+      const uint32_t q_addr = smem_u32(sQ), k_addr = smem_u32(sK), v_addr = smem_u32(sV);
+      auto issue_qk = [&](int t, int ks) {
+        const uint32_t qa = q_addr + t * TILE_BYTES, ka = k_addr + ks * TILE_BYTES;
+#pragma unroll
+        for (int k = 0; k < HD / 16; ++k) {
+          const uint32_t off = (k >> 2) * 16384 + (k & 3) * 32;
+          umma_ss(tmem_base + t * 128, make_sdesc_sw128(qa + off, 16, 1024), make_sdesc_sw128(ka + off, 16, 1024), idesc_qk,
+                  k != 0 ? 1u : 0u);
+        }
+        umma_commit(&sfull[t]);
+      };
+      auto issue_pv = [&](int t, int vs, bool acc) {
+        const uint32_t va = v_addr + vs * TILE_BYTES;
+#pragma unroll
+        for (int k = 0; k < KT / 16; ++k)
+          umma_ts(tmem_base + 256 + t * 128, tmem_base + t * 128 + k * 8, make_sdesc_sw128(va + k * 2048, 16384, 1024), idesc_pv,
+                  (acc || k != 0) ? 1u : 0u);
+      };
+      mbar_wait(qfull, 0);
+      mbar_wait(&kfull[0], 0);
+      tc_fence_after();
+      issue_qk(0, 0);
+      issue_qk(1, 0);
+      umma_commit(&kempty[0]);
+      for (int j = 0; j < n_kv; ++j) {
+        const int s = j % KV_STAGES;
+        const uint32_t ph = (j / KV_STAGES) & 1;
+        const bool more = j + 1 < n_kv;
+        const int s1 = (j + 1) % KV_STAGES;
+        const uint32_t ph1 = ((j + 1) / KV_STAGES) & 1;
+        mbar_wait(&vfull[s], ph);
+        mbar_wait(&pfull[0], j & 1);
+        tc_fence_after();
+        issue_pv(0, s, j > 0);
+        if (more) {
+          mbar_wait(&kfull[s1], ph1);
+          tc_fence_after();
+          issue_qk(0, s1);
+        }
+        mbar_wait(&pfull[1], j & 1);
+        tc_fence_after();
+        issue_pv(1, s, j > 0);
+        umma_commit(&vempty[s]);
+        if (more) {
+          issue_qk(1, s1);
+          umma_commit(&kempty[s1]);
+        }
+      }
+      umma_commit(ofull);
+    }
+  } else {
+    // ------------------------------- softmax + epilogue -------------------------------
+    const int t = warp >> 2;        // Q tile handled by this warpgroup
+    const int quad = warp & 3;      // TMEM lane quadrant
+    const int row = q0 + t * QT + quad * 32 + lane;
+    const uint32_t lane_off = (uint32_t)(quad * 32) << 16;
+    const uint32_t s_addr = tmem_base + t * 128 + lane_off;
+    const uint32_t o_addr = tmem_base + 256 + t * 128 + lane_off;
+    float m_used = -INFINITY;  // max the exponentials are currently relative to (log2 domain)
+    float l_sum = 0.f;
+    for (int j = 0; j < n_kv; ++j) {
+      mbar_wait(&sfull[t], j & 1);
+      tc_fence_after();
+      uint32_t r[4][32];
+#pragma unroll
+      for (int c = 0; c < 4; ++c) tmem_ld32(s_addr + c * 32, r[c]);
+      tmem_wait_ld();
+      const int valid = p.Lk - j * KT;  // columns >= valid are padding (TMA zero fill)
+      float mx = -INFINITY;
+#pragma unroll
+      for (int c = 0; c < 4; ++c)
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          float v = __uint_as_float(r[c][i]);
+          if (valid < KT && c * 32 + i >= valid) {
+            v = -INFINITY;
+            r[c][i] = __float_as_uint(v);
+          }
+          mx = fmaxf(mx, v);
+        }
+      const float m_new = fmaxf(m_used, mx * p.scale_log2);
+      if (j == 0) {
+        m_used = m_new;
+      } else if (__any_sync(0xffffffffu, m_new > m_used + 8.0f)) {
+        // rescale O (warp-uniform branch: tcgen05.ld/st are warp-collective)
+        const float alpha = fast_exp2(m_used - m_new);
+        l_sum *= alpha;
+        m_used = m_new;
+#pragma unroll 1
+        for (int c = 0; c < 4; ++c) {
+          uint32_t o[32];
+          tmem_ld32(o_addr + c * 32, o);
+          tmem_wait_ld();
+#pragma unroll
+          for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+          tmem_st32(o_addr + c * 32, o);
+        }
+      }
+      const float neg_m = -m_used;
+#pragma unroll
+      for (int c = 0; c < 4; c += 2) {
+        uint32_t pk[32];
+#pragma unroll
+        for (int i = 0; i < 32; i += 2) {
+          float a0 = fast_exp2(fmaf(__uint_as_float(r[c][i]), p.scale_log2, neg_m));
+          float a1 = fast_exp2(fmaf(__uint_as_float(r[c][i + 1]), p.scale_log2, neg_m));
+          float b0 = fast_exp2(fmaf(__uint_as_float(r[c + 1][i]), p.scale_log2, neg_m));
+          float b1 = fast_exp2(fmaf(__uint_as_float(r[c + 1][i + 1]), p.scale_log2, neg_m));
+          l_sum += (a0 + a1) + (b0 + b1);
+          pk[i >> 1] = pack_bf16x2(a0, a1);
+          pk[16 + (i >> 1)] = pack_bf16x2(b0, b1);
+        }
+        tmem_st32(s_addr + c * 16, pk);  // P columns [32*(c/2), +32) hold keys [64*(c/2), +64)
+      }
+      tmem_wait_st();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&pfull[t]);
+    }
+    // epilogue: O / l -> bf16 -> global; LSE
+    mbar_wait(ofull, 0);
+    tc_fence_after();
+    const float inv_l = 1.0f / l_sum;
+    const bool row_ok = row < p.Lq;
+    __nv_bfloat16* orow = p.o + (int64_t)row * p.o_ld_tok + (int64_t)head * p.o_ld_head;
+#pragma unroll 1
+    for (int c = 0; c < 4; ++c) {
+      uint32_t o[32];
+      tmem_ld32(o_addr + c * 32, o);
+      tmem_wait_ld();
+      if (row_ok) {
+#pragma unroll
+        for (int i = 0; i < 32; i += 8) {
+          uint4 v;
+          v.x = pack_bf16x2(__uint_as_float(o[i]) * inv_l, __uint_as_float(o[i + 1]) * inv_l);
+          v.y = pack_bf16x2(__uint_as_float(o[i + 2]) * inv_l, __uint_as_float(o[i + 3]) * inv_l);
+          v.z = pack_bf16x2(__uint_as_float(o[i + 4]) * inv_l, __uint_as_float(o[i + 5]) * inv_l);
+          v.w = pack_bf16x2(__uint_as_float(o[i + 6]) * inv_l, __uint_as_float(o[i + 7]) * inv_l);
+          *reinterpret_cast<uint4*>(orow + c * 32 + i) = v;
+        }
+      }
+      __syncwarp();
+    }
+    if (row_ok && p.lse) p.lse[(int64_t)head * p.Lq + row] = (m_used + log2f(l_sum)) * 0.6931471805599453f;
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 9) {
+    tc_fence_after();
+    tmem_dealloc<512>(tmem_base);
+  }
+}
+
+}  // namespace prfl
+
+using namespace prfl;
+
+extern "C" int prfl_attn_fwd(const void* q, int64_t q_ld_tok, int64_t q_ld_head, const void* k, int64_t k_ld_tok,
+                             int64_t k_ld_head, const void* v, int64_t v_ld_tok, int64_t v_ld_head, void* o, int64_t o_ld_tok,
+                             int64_t o_ld_head, float* lse, int Lq, int Lk, int H, float scale, prfl_stream_t stream) {
+  PRFL_CHECK_ARCH();
+  PRFL_REQUIRE(Lq > 0 && Lk > 0 && H > 0, PRFL_E_SHAPE, "attn_fwd: Lq=%d Lk=%d H=%d", Lq, Lk, H);
+  PRFL_REQUIRE(q_ld_tok % 8 == 0 && q_ld_head % 8 == 0 && k_ld_tok % 8 == 0 && k_ld_head % 8 == 0 && v_ld_tok % 8 == 0 &&
+                   v_ld_head % 8 == 0 && o_ld_tok % 8 == 0 && o_ld_head % 8 == 0 && (reinterpret_cast<uintptr_t>(o) & 15) == 0,
+               PRFL_E_ALIGN, "attn_fwd: strides must be multiples of 8 elements, pointers 16-byte aligned");
+  CUtensorMap tmQ, tmK, tmV;
+  int rc = make_tmap_3d(&tmQ, q, HD, (uint64_t)Lq, (uint64_t)H, (uint64_t)q_ld_tok * 2, (uint64_t)q_ld_head * 2, 64, QT, 1, 1);
+  if (rc != PRFL_OK) return rc;
+  rc = make_tmap_3d(&tmK, k, HD, (uint64_t)Lk, (uint64_t)H, (uint64_t)k_ld_tok * 2, (uint64_t)k_ld_head * 2, 64, KT, 1, 1);
+  if (rc != PRFL_OK) return rc;
+  rc = make_tmap_3d(&tmV, v, HD, (uint64_t)Lk, (uint64_t)H, (uint64_t)v_ld_tok * 2, (uint64_t)v_ld_head * 2, 64, KT, 1, 1);
+  if (rc != PRFL_OK) return rc;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM);
+    if (e != cudaSuccess) return cuda_fail(e, "attn_fwd: cudaFuncSetAttribute");
+    attr_set = true;
+  }
+  AttnFwdParams p;
+  p.o = (__nv_bfloat16*)o; p.o_ld_tok = o_ld_tok; p.o_ld_head = o_ld_head; p.lse = lse; p.Lq = Lq; p.Lk = Lk;
+  p.scale_log2 = scale * 1.4426950408889634f;
+  dim3 grid((Lq + 2 * QT - 1) / (2 * QT), H);
+  attn_fwd_kernel<<<grid, ATT_THREADS, ATT_SMEM, (cudaStream_t)stream>>>(tmQ, tmK, tmV, p);
+  count_launch();
+  PRFL_LAUNCH_CHECK("attn_fwd");
+  return PRFL_OK;
+}

@@ -1,0 +1,505 @@
+"""B200-native Wan-DiT with the reference's module API (diffusers_lite/wan/modules/model.py).
+
+Same class names, constructor signatures, parameter names (state-dict keys) and forward signatures as
+the reference `WanModel` / `WanAttentionBlock` / `WanSelfAttention` / `Wan{T2V,I2V}CrossAttention` /
+`WanRMSNorm` / `WanLayerNorm` / `Head` / `MLPProj`, so reference checkpoints load and the reference
+trainers can call it unchanged; but every forward runs hand-written sm_100a kernels through the C ABI
+(prfl_b200.ops) instead of ATen / cuBLAS / flash-attn.  There is no CPU or PyTorch fallback: on a
+machine without the CUDA library these forwards raise.
+
+Precision choreography kept from the reference: fp32 residual stream, bf16
+GEMM/attention operands with fp32 accumulation, RMSNorm over the full channel dim with the bf16 rounding
+before the weight multiply, RoPE angles from float64, fp32 time-embedding path and fp32 head.
+
+Per block (sequence of C-ABI calls, B = 1 sample at a time, M = local tokens):
+  ln_mod -> gemm(QKV fused, N=3C) -> rmsnorm_rope(q), rmsnorm_rope(k) -> [a2a] -> attn_fwd -> [a2a]
+  -> gemm(o, gated residual epilogue) -> ln_mod(affine) -> gemm(cross q) -> rmsnorm -> gemm(ctx KV)
+  -> rmsnorm -> attn_fwd (x2 for i2v) -> gemm(cross o, residual epilogue) -> ln_mod
+  -> gemm(ffn.0, GELU epilogue) -> gemm(ffn.2, gated residual epilogue)
+"""
+from __future__ import annotations
+
+import math
+from typing import List, Optional, Sequence
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from . import ops
+from .parallel import get_sequence_parallel_state, nccl_info, ulysses_gather_tokens, ulysses_scatter_tokens, all_gather
+from .rope import rope_tables
+
+__all__ = ["WanModel", "WanAttentionBlock", "WanSelfAttention", "WanT2VCrossAttention", "WanI2VCrossAttention",
+           "WanRMSNorm", "WanLayerNorm", "Head", "MLPProj", "sinusoidal_embedding_1d", "rope_params"]
+
+T5_CONTEXT_TOKEN_NUMBER = 512
+
+
+# ------------------------------------------------------------------------------------------------
+# bf16 operand cache: fp32 master parameters -> bf16 copies, refreshed when the parameter changes
+# (what torch.autocast re-does on every Linear call in the reference).
+# ------------------------------------------------------------------------------------------------
+class _OperandCache:
+    def __init__(self):
+        self._store = {}
+
+    def get(self, key, params: Sequence[torch.Tensor], build):
+        ver = tuple((p.data_ptr(), p._version) for p in params)
+        hit = self._store.get(key)
+        if hit is not None and hit[0] == ver:
+            return hit[1]
+        val = build()
+        self._store[key] = (ver, val)
+        return val
+
+    def clear(self):
+        self._store.clear()
+
+
+def _cat_bf16(ws: Sequence[torch.Tensor]) -> torch.Tensor:
+    w = torch.cat([p.detach().reshape(p.shape[0], -1) for p in ws], dim=0).float().contiguous()
+    return ops.cast_bf16(w)
+
+
+def _cat_f32(bs: Sequence[torch.Tensor]) -> torch.Tensor:
+    # autocast casts the bias to bf16 before the addmm; keep that rounding, store as fp32 for the epilogue
+    return torch.cat([b.detach().float() for b in bs]).bfloat16().float().contiguous()
+
+
+class _Linear(nn.Linear):
+    """nn.Linear whose forward is the tcgen05 GEMM (bf16 operands, fp32 accumulate, bf16 out)."""
+
+    def operands(self):
+        cache = self.__dict__.setdefault("_prfl_cache", _OperandCache())
+        w = cache.get("w", [self.weight], lambda: _cat_bf16([self.weight]))
+        b = None if self.bias is None else cache.get("b", [self.bias], lambda: _cat_f32([self.bias]))
+        return w, b
+
+    def forward(self, x):
+        w, b = self.operands()
+        shp = x.shape
+        x2 = x.reshape(-1, shp[-1])
+        if x2.dtype != torch.bfloat16:
+            x2 = x2.to(torch.bfloat16)
+        y = ops.gemm(x2.contiguous(), w, bias=b, epi=ops.EPI_BF16)
+        return y.view(*shp[:-1], -1)
+
+
+def sinusoidal_embedding_1d(dim, position):
+    """model.py:22-32 (float64)."""
+    assert dim % 2 == 0
+    half = dim // 2
+    position = position.type(torch.float64)
+    sinusoid = torch.outer(position, torch.pow(10000, -torch.arange(half).to(position).div(half)))
+    return torch.cat([torch.cos(sinusoid), torch.sin(sinusoid)], dim=1)
+
+
+def rope_params(max_seq_len, dim, theta=10000):
+    """model.py:35-43 — kept for API parity (`WanModel.freqs`); the kernels use rope.rope_tables."""
+    assert dim % 2 == 0
+    freqs = torch.outer(torch.arange(max_seq_len),
+                        1.0 / torch.pow(theta, torch.arange(0, dim, 2).to(torch.float64).div(dim)))
+    return torch.polar(torch.ones_like(freqs), freqs)
+
+
+class WanRMSNorm(nn.Module):
+    """model.py:106-122.  forward() accepts a bf16 [.., C] tensor and normalises over all C channels."""
+
+    def __init__(self, dim, eps=1e-5):
+        super().__init__()
+        self.dim = dim
+        self.eps = eps
+        self.weight = nn.Parameter(torch.ones(dim))
+
+    def forward(self, x):
+        shp = x.shape
+        x2 = x.reshape(-1, shp[-1]).to(torch.bfloat16).contiguous()
+        out = torch.empty_like(x2)
+        ops.rmsnorm_rope_(x2, self.weight.detach().float(), None, None, self.eps, out=out)
+        return out.view(shp)
+
+
+class WanLayerNorm(nn.LayerNorm):
+    """model.py:125-135.  fp32 in -> bf16 out (the consumer is always a bf16 GEMM)."""
+
+    def __init__(self, dim, eps=1e-6, elementwise_affine=False):
+        super().__init__(dim, elementwise_affine=elementwise_affine, eps=eps)
+
+    def forward(self, x, shift=None, scale=None, round_bf16=False):
+        shp = x.shape
+        x2 = x.reshape(-1, shp[-1]).float().contiguous()
+        g = self.weight.detach().float() if self.elementwise_affine else None
+        b = self.bias.detach().float() if self.elementwise_affine else None
+        return ops.ln_mod(x2, shift, scale, g, b, self.eps, round_bf16).view(shp)
+
+
+def _grid_list(grid_sizes):
+    return [tuple(int(v) for v in g) for g in (grid_sizes.tolist() if torch.is_tensor(grid_sizes) else grid_sizes)]
+
+
+class WanSelfAttention(nn.Module):
+    """model.py:138-201."""
+
+    def __init__(self, dim, num_heads, window_size=(-1, -1), qk_norm=True, eps=1e-6):
+        assert dim % num_heads == 0
+        super().__init__()
+        self.dim = dim
+        self.num_heads = num_heads
+        self.head_dim = dim // num_heads
+        assert self.head_dim == 128, "prfl_b200 attention kernels are head_dim 128 only"
+        self.window_size = window_size
+        self.qk_norm = qk_norm
+        self.eps = eps
+        self.q = _Linear(dim, dim)
+        self.k = _Linear(dim, dim)
+        self.v = _Linear(dim, dim)
+        self.o = _Linear(dim, dim)
+        self.norm_q = WanRMSNorm(dim, eps=eps) if qk_norm else nn.Identity()
+        self.norm_k = WanRMSNorm(dim, eps=eps) if qk_norm else nn.Identity()
+
+    def _qkv_operands(self):
+        cache = self.__dict__.setdefault("_prfl_cache", _OperandCache())
+        ws = [self.q.weight, self.k.weight, self.v.weight]
+        bs = [self.q.bias, self.k.bias, self.v.bias]
+        return cache.get("wqkv", ws, lambda: _cat_bf16(ws)), cache.get("bqkv", bs, lambda: _cat_f32(bs))
+
+    def attend(self, h, seq_lens, grid_sizes):
+        """h: [B, s, C] bf16 (already normalised + modulated) -> attention output [B, s, C] bf16,
+        BEFORE the output projection (the caller fuses `o` with the gated residual)."""
+        assert self.qk_norm, "qk_norm=False is not on the reference path"
+        b, s, C = h.shape
+        n, d = self.num_heads, self.head_dim
+        wqkv, bqkv = self._qkv_operands()
+        sp = get_sequence_parallel_state()
+        P = nccl_info.sp_size if sp else 1
+        rank = nccl_info.rank_within_group if sp else 0
+        grids = _grid_list(grid_sizes)
+        outs = []
+        for i in range(b):
+            qkv = ops.gemm(h[i], wqkv, bias=bqkv, epi=ops.EPI_BF16)            # [s, 3C]
+            f, hh, ww = grids[i]
+            seq_len = f * hh * ww
+            cos, sin = rope_tables(grids[i], h.device, d, pad_to=s * P)
+            n_rot = s if sp else min(seq_len, s)
+            ops.rmsnorm_rope_(qkv[:, :C], self.norm_q.weight.detach().float(), cos, sin, self.eps, n_rot, rank * s)
+            ops.rmsnorm_rope_(qkv[:, C:2 * C], self.norm_k.weight.detach().float(), cos, sin, self.eps, n_rot, rank * s)
+            q3, k3, v3 = (qkv[:, j * C:(j + 1) * C].unflatten(1, (n, d)) for j in range(3))
+            klen = int(seq_lens[i])
+            if not sp:
+                o = ops.attn_fwd(q3, k3[:klen], v3[:klen])                        # [s, n, d]
+            else:
+                qg, kg, vg = (ulysses_scatter_tokens(t, P) for t in (q3, k3, v3))  # [s*P, n/P, d]
+                og = ops.attn_fwd(qg, kg[:klen], vg[:klen])
+                o = ulysses_gather_tokens(og, P)                                 # [s, n, d]
+            outs.append(o.reshape(s, C))
+        return torch.stack(outs)
+
+    def forward(self, x, seq_lens, grid_sizes, freqs=None):
+        """Reference signature (model.py:163).  x: [B, L, C]; returns o(attention) as bf16 [B, L, C]."""
+        h = x if x.dtype == torch.bfloat16 else x.to(torch.bfloat16)
+        return self.o(self.attend(h.contiguous(), seq_lens, grid_sizes))
+
+
+class WanT2VCrossAttention(WanSelfAttention):
+    """model.py:204-226."""
+
+    def _kv_operands(self, names=("k", "v")):
+        cache = self.__dict__.setdefault("_prfl_cache", _OperandCache())
+        ws = [getattr(self, nm).weight for nm in names]
+        bs = [getattr(self, nm).bias for nm in names]
+        return (cache.get("w" + "".join(names), ws, lambda: _cat_bf16(ws)),
+                cache.get("b" + "".join(names), bs, lambda: _cat_f32(bs)))
+
+    def _attend_ctx(self, q3, ctx, names, norm):
+        C, n, d = self.dim, self.num_heads, self.head_dim
+        wkv, bkv = self._kv_operands(names)
+        kv = ops.gemm(ctx, wkv, bias=bkv, epi=ops.EPI_BF16)                       # [Lc, 2C]
+        ops.rmsnorm_rope_(kv[:, :C], norm.weight.detach().float(), None, None, self.eps)
+        return ops.attn_fwd(q3, kv[:, :C].unflatten(1, (n, d)), kv[:, C:].unflatten(1, (n, d)))
+
+    def attend(self, h, context, context_lens=None):
+        assert context_lens is None, "the reference path passes context_lens=None (model.py:597)"
+        b, s, C = h.shape
+        n, d = self.num_heads, self.head_dim
+        wq, bq = self.q.operands()
+        outs = []
+        for i in range(b):
+            q = ops.gemm(h[i], wq, bias=bq, epi=ops.EPI_BF16)
+            ops.rmsnorm_rope_(q, self.norm_q.weight.detach().float(), None, None, self.eps)
+            o = self._attend_ctx(q.unflatten(1, (n, d)), context[i], ("k", "v"), self.norm_k)
+            outs.append(o.reshape(s, C))
+        return torch.stack(outs)
+
+    def forward(self, x, context, context_lens):
+        h = x if x.dtype == torch.bfloat16 else x.to(torch.bfloat16)
+        return self.o(self.attend(h.contiguous(), context.to(torch.bfloat16).contiguous(), context_lens))
+
+
+class WanI2VCrossAttention(WanT2VCrossAttention):
+    """model.py:229-271: CLIP image tokens first, text = last 512 tokens; two attentions, summed."""
+
+    def __init__(self, dim, num_heads, window_size=(-1, -1), qk_norm=True, eps=1e-6):
+        super().__init__(dim, num_heads, window_size, qk_norm, eps)
+        self.k_img = _Linear(dim, dim)
+        self.v_img = _Linear(dim, dim)
+        self.norm_k_img = WanRMSNorm(dim, eps=eps) if qk_norm else nn.Identity()
+
+    def attend(self, h, context, context_lens=None):
+        assert context_lens is None
+        b, s, C = h.shape
+        n, d = self.num_heads, self.head_dim
+        n_img = context.shape[1] - T5_CONTEXT_TOKEN_NUMBER
+        wq, bq = self.q.operands()
+        outs = []
+        for i in range(b):
+            q = ops.gemm(h[i], wq, bias=bq, epi=ops.EPI_BF16)
+            ops.rmsnorm_rope_(q, self.norm_q.weight.detach().float(), None, None, self.eps)
+            q3 = q.unflatten(1, (n, d))
+            o_img = self._attend_ctx(q3, context[i, :n_img].contiguous(), ("k_img", "v_img"), self.norm_k_img)
+            o_txt = self._attend_ctx(q3, context[i, n_img:].contiguous(), ("k", "v"), self.norm_k)
+            outs.append((o_txt + o_img).reshape(s, C))                            # model.py:269 (bf16 add)
+        return torch.stack(outs)
+
+
+WAN_CROSSATTENTION_CLASSES = {"t2v_cross_attn": WanT2VCrossAttention, "i2v_cross_attn": WanI2VCrossAttention}
+
+
+class WanAttentionBlock(nn.Module):
+    """model.py:280-359."""
+
+    def __init__(self, cross_attn_type, dim, ffn_dim, num_heads, window_size=(-1, -1), qk_norm=True,
+                 cross_attn_norm=False, eps=1e-6):
+        super().__init__()
+        self.dim = dim
+        self.ffn_dim = ffn_dim
+        self.num_heads = num_heads
+        self.window_size = window_size
+        self.qk_norm = qk_norm
+        self.cross_attn_norm = cross_attn_norm
+        self.eps = eps
+        self.norm1 = WanLayerNorm(dim, eps)
+        self.self_attn = WanSelfAttention(dim, num_heads, window_size, qk_norm, eps)
+        self.norm3 = WanLayerNorm(dim, eps, elementwise_affine=True) if cross_attn_norm else nn.Identity()
+        self.cross_attn = WAN_CROSSATTENTION_CLASSES[cross_attn_type](dim, num_heads, (-1, -1), qk_norm, eps)
+        self.norm2 = WanLayerNorm(dim, eps)
+        self.ffn = nn.Sequential(_Linear(dim, ffn_dim), nn.GELU(approximate="tanh"), _Linear(ffn_dim, dim))
+        self.modulation = nn.Parameter(torch.randn(1, 6, dim) / dim ** 0.5)
+
+    def forward(self, x, e, seq_lens, grid_sizes, freqs, context, context_lens, first_block_bf16_input=False):
+        """x: [B, L, C] fp32 residual stream (updated IN PLACE and returned), e: [B, 6, C] fp32,
+        context: [B, Lc, C] bf16.  `first_block_bf16_input` reproduces the reference's extra bf16
+        rounding of norm1's output in block 0, whose input is bf16 (model.py:345 with x.dtype == bf16)."""
+        assert e.dtype == torch.float32 and x.dtype == torch.float32 and x.is_contiguous()
+        B, L, C = x.shape
+        em = (self.modulation.detach().float() + e).contiguous()                   # [B, 6, C]
+        ctx = context if context.dtype == torch.bfloat16 else context.to(torch.bfloat16)
+        for i in range(B):
+            xi = x[i]
+            ei = em[i]
+            h = self.norm1(xi, shift=ei[0], scale=ei[1], round_bf16=first_block_bf16_input)
+            a = self.self_attn.attend(h.unsqueeze(0), seq_lens[i:i + 1], grid_sizes[i:i + 1])[0]
+            wo, bo = self.self_attn.o.operands()
+            ops.gemm(a, wo, bias=bo, epi=ops.EPI_RESIDUAL, out=xi, gate=ei[2])      # x += e2 * o(attn)
+            h = self.norm3(xi) if self.cross_attn_norm else ops.cast_bf16(xi)
+            a = self.cross_attn.attend(h.unsqueeze(0), ctx[i:i + 1], context_lens)[0]
+            wo, bo = self.cross_attn.o.operands()
+            ops.gemm(a, wo, bias=bo, epi=ops.EPI_RESIDUAL, out=xi)                  # x += o(cross)
+            h = self.norm2(xi, shift=ei[3], scale=ei[4])
+            w1, b1 = self.ffn[0].operands()
+            w2, b2 = self.ffn[2].operands()
+            f = ops.gemm(h, w1, bias=b1, epi=ops.EPI_BF16_GELU)
+            ops.gemm(f, w2, bias=b2, epi=ops.EPI_RESIDUAL, out=xi, gate=ei[5])      # x += e5 * ffn
+        return x
+
+
+class Head(nn.Module):
+    """model.py:362-389 — fp32 throughout."""
+
+    def __init__(self, dim, out_dim, patch_size, eps=1e-6):
+        super().__init__()
+        self.dim = dim
+        self.out_dim = out_dim
+        self.patch_size = patch_size
+        self.eps = eps
+        out_dim = math.prod(patch_size) * out_dim
+        self.norm = WanLayerNorm(dim, eps)
+        self.head = nn.Linear(dim, out_dim)
+        self.modulation = nn.Parameter(torch.randn(1, 2, dim) / dim ** 0.5)
+
+    def forward(self, x, e):
+        assert e.dtype == torch.float32
+        m = (self.modulation.detach().float() + e.unsqueeze(1)).chunk(2, dim=1)
+        h = F.layer_norm(x.float(), (self.dim,), None, None, self.eps) * (1 + m[1]) + m[0]
+        return F.linear(h, self.head.weight.float(), self.head.bias.float())
+
+
+class MLPProj(nn.Module):
+    """model.py:392-410.  [B, 257, 1280] CLIP features -> [B, 257, dim]; ~0.01 % of the FLOPs, kept in PyTorch
+     except the two Linears which go through the tcgen05 GEMM."""
+
+    def __init__(self, in_dim, out_dim, flf_pos_emb=False):
+        super().__init__()
+        self.proj = nn.Sequential(nn.LayerNorm(in_dim), _Linear(in_dim, in_dim), nn.GELU(), _Linear(in_dim, out_dim),
+                                  nn.LayerNorm(out_dim))
+        if flf_pos_emb:
+            self.emb_pos = nn.Parameter(torch.zeros(1, 257 * 2, 1280))
+
+    def forward(self, image_embeds):
+        if hasattr(self, "emb_pos"):
+            bs, n, d = image_embeds.shape
+            image_embeds = image_embeds.view(-1, 2 * n, d) + self.emb_pos
+        p = self.proj
+        h = F.layer_norm(image_embeds.float(), p[0].normalized_shape, p[0].weight.float(), p[0].bias.float(), p[0].eps)
+        h = p[1](h)
+        h = F.gelu(h.float()).to(torch.bfloat16)
+        h = p[3](h)
+        return F.layer_norm(h.float(), p[4].normalized_shape, p[4].weight.float(), p[4].bias.float(), p[4].eps)
+
+
+class WanModel(nn.Module):
+    """model.py:413-729.  Drop-in: same __init__ / forward signature, attributes (`blocks`, `head`, `freqs`,
+    `enable_teacache`, `_no_split_modules`, `config`) and state-dict keys."""
+
+    ignore_for_config = ["patch_size", "cross_attn_norm", "qk_norm", "text_dim", "window_size"]
+    _no_split_modules = ["WanAttentionBlock"]
+    enable_teacache = False          # class attribute, as the trainers set it (train_pavrm.py:237)
+
+    def __init__(self, model_type="t2v", patch_size=(1, 2, 2), text_len=512, in_dim=16, dim=2048, ffn_dim=8192,
+                 freq_dim=256, text_dim=4096, out_dim=16, num_heads=16, num_layers=32, window_size=(-1, -1),
+                 qk_norm=True, cross_attn_norm=True, eps=1e-6):
+        super().__init__()
+        assert model_type in ["t2v", "i2v", "flf2v"]
+        assert tuple(patch_size) == (1, 2, 2), "prfl_b200 patchify kernels implement patch_size (1, 2, 2)"
+        self.config = dict(model_type=model_type, patch_size=tuple(patch_size), text_len=text_len, in_dim=in_dim, dim=dim,
+                           ffn_dim=ffn_dim, freq_dim=freq_dim, text_dim=text_dim, out_dim=out_dim, num_heads=num_heads,
+                           num_layers=num_layers, window_size=tuple(window_size), qk_norm=qk_norm,
+                           cross_attn_norm=cross_attn_norm, eps=eps)
+        self.model_type = model_type
+        self.patch_size = tuple(patch_size)
+        self.text_len = text_len
+        self.in_dim = in_dim
+        self.dim = dim
+        self.ffn_dim = ffn_dim
+        self.freq_dim = freq_dim
+        self.text_dim = text_dim
+        self.out_dim = out_dim
+        self.num_heads = num_heads
+        self.num_layers = num_layers
+        self.window_size = window_size
+        self.qk_norm = qk_norm
+        self.cross_attn_norm = cross_attn_norm
+        self.eps = eps
+
+        self.patch_embedding = nn.Conv3d(in_dim, dim, kernel_size=patch_size, stride=patch_size)
+        self.text_embedding = nn.Sequential(_Linear(text_dim, dim), nn.GELU(approximate="tanh"), _Linear(dim, dim))
+        self.time_embedding = nn.Sequential(nn.Linear(freq_dim, dim), nn.SiLU(), nn.Linear(dim, dim))
+        self.time_projection = nn.Sequential(nn.SiLU(), nn.Linear(dim, dim * 6))
+        cross_attn_type = "t2v_cross_attn" if model_type == "t2v" else "i2v_cross_attn"
+        self.blocks = nn.ModuleList([
+            WanAttentionBlock(cross_attn_type, dim, ffn_dim, num_heads, window_size, qk_norm, cross_attn_norm, eps)
+            for _ in range(num_layers)])
+        self.head = Head(dim, out_dim, patch_size, eps)
+        assert (dim % num_heads) == 0 and (dim // num_heads) % 2 == 0
+        d = dim // num_heads
+        self.freqs = torch.cat([rope_params(1024, d - 4 * (d // 6)), rope_params(1024, 2 * (d // 6)),
+                                rope_params(1024, 2 * (d // 6))], dim=1)
+        if model_type in ("i2v", "flf2v"):
+            self.img_emb = MLPProj(1280, dim, flf_pos_emb=model_type == "flf2v")
+        self.init_weights()
+
+    # -- embeddings ---------------------------------------------------------------------------
+    def _patch_operands(self):
+        cache = self.__dict__.setdefault("_prfl_cache", _OperandCache())
+        w = cache.get("wp", [self.patch_embedding.weight], lambda: _cat_bf16([self.patch_embedding.weight]))
+        b = cache.get("bp", [self.patch_embedding.bias], lambda: _cat_f32([self.patch_embedding.bias]))
+        return w, b
+
+    def _embed_context(self, context, clip_fea):
+        dev = self.patch_embedding.weight.device
+        ctx = torch.stack([torch.cat([u, u.new_zeros(self.text_len - u.size(0), u.size(1))]) for u in context])
+        ctx = ctx.to(device=dev, dtype=torch.bfloat16)
+        w0, b0 = self.text_embedding[0].operands()
+        w2, b2 = self.text_embedding[2].operands()
+        B = ctx.shape[0]
+        h = ops.gemm(ctx.view(B * self.text_len, -1), w0, bias=b0, epi=ops.EPI_BF16_GELU)
+        ctx = ops.gemm(h, w2, bias=b2, epi=ops.EPI_BF16).view(B, self.text_len, self.dim)
+        if clip_fea is not None:
+            ctx = torch.cat([self.img_emb(clip_fea.to(dev)).to(torch.bfloat16), ctx], dim=1)
+        return ctx
+
+    def forward(self, x, t, context, seq_len, clip_fea=None, y=None, cond_flag=False, output_features=False,
+                selected_layers=[20, 30, 40]):
+        """Same contract as the reference (model.py:534-681): x list of [C_in, F, H, W], t [B], context list of
+        [L, C]; returns a list of [C_out, F, H, W] fp32 tensors, or with output_features the list of
+        [B, L, dim] fp32 features after the selected (1-based) blocks."""
+        if self.model_type in ("i2v", "flf2v"):
+            assert clip_fea is not None and y is not None
+        assert not self.enable_teacache, "teacache is an inference-time heuristic outside this path"
+        dev = self.patch_embedding.weight.device
+        wp, bp = self._patch_operands()
+        embs, grids = [], []
+        for i, u in enumerate(x):
+            yi = None if y is None else y[i].to(device=dev, dtype=torch.float32).contiguous()
+            patches = ops.patchify(u.to(device=dev, dtype=torch.float32).contiguous(), yi)
+            embs.append(ops.gemm(patches, wp, bias=bp, epi=ops.EPI_BF16))            # [L_i, dim] bf16, like the autocast conv
+            grids.append((u.shape[1] // self.patch_size[0], u.shape[2] // self.patch_size[1], u.shape[3] // self.patch_size[2]))
+        seq_lens = torch.tensor([e_.size(0) for e_ in embs], dtype=torch.long)
+        grid_sizes = torch.tensor(grids, dtype=torch.long)
+        assert int(seq_lens.max()) <= seq_len
+        xs = torch.zeros(len(embs), seq_len, self.dim, dtype=torch.float32, device=dev)
+        for i, e_ in enumerate(embs):
+            xs[i, :e_.size(0)] = e_
+
+        # time embeddings — fp32 (model.py:589-594); tiny, PyTorch
+        tt = t.to(dev)
+        te = self.time_embedding
+        e = F.linear(sinusoidal_embedding_1d(self.freq_dim, tt).float(), te[0].weight.float(), te[0].bias.float())
+        e = F.linear(F.silu(e), te[2].weight.float(), te[2].bias.float())
+        tp = self.time_projection[1]
+        e0 = F.linear(F.silu(e), tp.weight.float(), tp.bias.float()).unflatten(1, (6, self.dim))
+
+        ctx = self._embed_context(context, clip_fea)
+
+        if get_sequence_parallel_state():
+            xs = torch.chunk(xs, nccl_info.sp_size, dim=1)[nccl_info.rank_within_group].contiguous()
+
+        features_list = []
+        for index, block in enumerate(self.blocks):
+            xs = block(xs, e=e0, seq_lens=seq_lens, grid_sizes=grid_sizes, freqs=self.freqs, context=ctx,
+                       context_lens=None, first_block_bf16_input=(index == 0))
+            if output_features and index + 1 in selected_layers:
+                features_list.append(all_gather(xs, dim=1) if get_sequence_parallel_state() else xs.clone())
+        if output_features:
+            return features_list
+
+        out = self.head(xs, e)
+        if get_sequence_parallel_state():
+            out = all_gather(out, dim=1)
+        return [u.float() for u in self.unpatchify(out, grid_sizes, self.out_dim)]
+
+    def unpatchify(self, x, grid_sizes, c):
+        """model.py:683-705."""
+        return [ops.unpatchify(u[:math.prod(g)].float().contiguous(), c, g) for u, g in zip(x, _grid_list(grid_sizes))]
+
+    def init_weights(self):
+        """model.py:707-729."""
+        for m in self.modules():
+            if isinstance(m, nn.Linear):
+                nn.init.xavier_uniform_(m.weight)
+                if m.bias is not None:
+                    nn.init.zeros_(m.bias)
+        nn.init.xavier_uniform_(self.patch_embedding.weight.flatten(1))
+        for m in self.text_embedding.modules():
+            if isinstance(m, nn.Linear):
+                nn.init.normal_(m.weight, std=.02)
+        for m in self.time_embedding.modules():
+            if isinstance(m, nn.Linear):
+                nn.init.normal_(m.weight, std=.02)
+        nn.init.zeros_(self.head.head.weight)
+
+    @classmethod
+    def from_config(cls, config):
+        keys = ("model_type", "patch_size", "text_len", "in_dim", "dim", "ffn_dim", "freq_dim", "text_dim", "out_dim",
+                "num_heads", "num_layers", "window_size", "qk_norm", "cross_attn_norm", "eps")
+        return cls(**{k: config[k] for k in keys if k in config})

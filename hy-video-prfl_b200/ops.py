@@ -1,0 +1,211 @@
+"""Tensor-level wrappers over the C ABI (include/prfl_b200.h).  PyTorch is used only to own device
+memory and to name the current stream; every FLOP / byte moved here happens in libprfl_b200.so."""
+from __future__ import annotations
+
+import math
+from typing import Optional, Tuple
+
+import torch
+
+from . import _lib
+from ._lib import EPI_BF16, EPI_BF16_DGELU, EPI_BF16_GELU, EPI_F32, EPI_RESIDUAL, check, lib
+
+bf16, f32 = torch.bfloat16, torch.float32
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _p(t: Optional[torch.Tensor]):
+    return None if t is None else t.data_ptr()
+
+
+def _req(t: torch.Tensor, dtype, name: str):
+    if not t.is_cuda:
+        raise _lib.PrflError(f"{name}: tensor must live on a CUDA device (prfl_b200 has no CPU path)")
+    if t.dtype != dtype:
+        raise _lib.PrflError(f"{name}: expected {dtype}, got {t.dtype}")
+
+
+# ------------------------------------------------------------------------------------------------
+def ln_mod(x: torch.Tensor, shift=None, scale=None, gamma=None, beta=None, eps: float = 1e-6,
+           round_bf16: bool = False, save_stats: bool = False):
+    """LayerNorm(+affine)(+modulate): fp32 [rows, C] -> bf16 [rows, C]  (model.py:345,352,353)."""
+    _req(x, f32, "ln_mod.x")
+    assert x.is_contiguous()
+    C = x.shape[-1]
+    rows = x.numel() // C
+    out = torch.empty(x.shape, dtype=bf16, device=x.device)
+    mean = torch.empty(rows, dtype=f32, device=x.device) if save_stats else None
+    rstd = torch.empty(rows, dtype=f32, device=x.device) if save_stats else None
+    for t, n in ((shift, "shift"), (scale, "scale"), (gamma, "gamma"), (beta, "beta")):
+        if t is not None:
+            _req(t, f32, "ln_mod." + n)
+            assert t.numel() == C and t.is_contiguous()
+    check(lib().prfl_ln_mod_fwd(_p(x), _p(shift), _p(scale), _p(gamma), _p(beta), _p(out), _p(mean), _p(rstd), rows, C,
+                                float(eps), int(round_bf16), _stream()), "prfl_ln_mod_fwd")
+    return (out, mean, rstd) if save_stats else out
+
+
+def rmsnorm_rope_(x: torch.Tensor, w: torch.Tensor, cos: Optional[torch.Tensor], sin: Optional[torch.Tensor],
+                  eps: float, n_rot: int = 0, pos0: int = 0, out: Optional[torch.Tensor] = None,
+                  save_rstd: bool = False):
+    """RMSNorm over the whole channel dim (+RoPE) on a bf16 [rows, C] view whose rows may be strided
+    (e.g. the q or k slice of a fused QKV buffer).  In place unless `out` is given."""
+    _req(x, bf16, "rmsnorm_rope.x")
+    _req(w, f32, "rmsnorm_rope.w")
+    assert x.dim() == 2 and x.stride(1) == 1
+    rows, C = x.shape
+    o = x if out is None else out
+    assert o.shape == x.shape and o.stride(1) == 1 and o.dtype == bf16
+    rstd = torch.empty(rows, dtype=f32, device=x.device) if save_rstd else None
+    if cos is not None:
+        _req(cos, f32, "rmsnorm_rope.cos")
+        assert cos.shape[-1] == 64 and cos.is_contiguous() and sin.is_contiguous()
+        assert pos0 + min(n_rot, rows) <= cos.shape[0]
+    check(lib().prfl_rmsnorm_rope_fwd(_p(x), x.stride(0), _p(w), _p(cos), _p(sin), _p(o), o.stride(0), _p(rstd), rows, C,
+                                      int(n_rot), int(pos0), float(eps), _stream()), "prfl_rmsnorm_rope_fwd")
+    return (o, rstd) if save_rstd else o
+
+
+def gemm(a: torch.Tensor, b: torch.Tensor, *, a_trans: bool = False, b_trans: bool = False,
+         bias: Optional[torch.Tensor] = None, epi: int = EPI_BF16, out: Optional[torch.Tensor] = None,
+         gate: Optional[torch.Tensor] = None, aux: Optional[torch.Tensor] = None, beta: bool = False) -> torch.Tensor:
+    """acc[m, n] = sum_k A(m, k) B(n, k) on tcgen05 with a fused epilogue.
+    a: [M, K] (or [K, M] if a_trans), b: [N, K] (or [K, N] if b_trans); inner stride 1, row stride free."""
+    _req(a, bf16, "gemm.a")
+    _req(b, bf16, "gemm.b")
+    assert a.dim() == 2 and b.dim() == 2 and a.stride(1) == 1 and b.stride(1) == 1
+    M, K = (a.shape[1], a.shape[0]) if a_trans else a.shape
+    N, Kb = (b.shape[1], b.shape[0]) if b_trans else b.shape
+    assert K == Kb, (a.shape, b.shape, a_trans, b_trans)
+    f32_out = epi in (EPI_F32, EPI_RESIDUAL)
+    if out is None:
+        assert epi != EPI_RESIDUAL and not beta
+        out = torch.empty(M, N, dtype=f32 if f32_out else bf16, device=a.device)
+    _req(out, f32 if f32_out else bf16, "gemm.out")
+    assert out.shape == (M, N) and out.stride(1) == 1
+    if bias is not None:
+        _req(bias, f32, "gemm.bias")
+        assert bias.numel() == N
+    if gate is not None:
+        _req(gate, f32, "gemm.gate")
+        assert gate.numel() == N
+    ldaux = 0
+    if aux is not None:
+        _req(aux, bf16, "gemm.aux")
+        assert aux.shape == (M, N) and aux.stride(1) == 1
+        ldaux = aux.stride(0)
+    check(lib().prfl_gemm_bf16(_p(a), a.stride(0), int(a_trans), _p(b), b.stride(0), int(b_trans), _p(out), out.stride(0),
+                               _p(bias), _p(gate), _p(aux), ldaux, M, N, K, epi, int(beta), _stream()), "prfl_gemm_bf16")
+    return out
+
+
+def attn_fwd(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, scale: Optional[float] = None,
+             out: Optional[torch.Tensor] = None, need_lse: bool = False):
+    """q: [Lq, H, 128], k/v: [Lk, H, 128] bf16 views (last stride 1; token / head strides free)."""
+    for t, n in ((q, "q"), (k, "k"), (v, "v")):
+        _req(t, bf16, "attn." + n)
+        assert t.dim() == 3 and t.shape[2] == 128 and t.stride(2) == 1, (n, t.shape, t.stride())
+    Lq, H, _ = q.shape
+    Lk = k.shape[0]
+    assert k.shape == v.shape and k.shape[1] == H
+    if out is None:
+        out = torch.empty(Lq, H, 128, dtype=bf16, device=q.device)
+    lse = torch.empty(H, Lq, dtype=f32, device=q.device) if need_lse else None
+    if scale is None:
+        scale = 1.0 / math.sqrt(128)
+    check(lib().prfl_attn_fwd(_p(q), q.stride(0), q.stride(1), _p(k), k.stride(0), k.stride(1), _p(v), v.stride(0), v.stride(1),
+                              _p(out), out.stride(0), out.stride(1), _p(lse), Lq, Lk, H, float(scale), _stream()), "prfl_attn_fwd")
+    return (out, lse) if need_lse else out
+
+
+def cast_bf16(src: torch.Tensor) -> torch.Tensor:
+    _req(src, f32, "cast.src")
+    assert src.is_contiguous()
+    dst = torch.empty(src.shape, dtype=bf16, device=src.device)
+    check(lib().prfl_cast_f32_bf16(_p(src), _p(dst), src.numel(), _stream()), "prfl_cast_f32_bf16")
+    return dst
+
+
+def patchify(x: torch.Tensor, y: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """[Cx, F, H, W] (+ [Cy, F, H, W]) fp32 -> [F*(H/2)*(W/2), (Cx+Cy)*4] bf16 (model.py:574-581)."""
+    _req(x, f32, "patchify.x")
+    assert x.is_contiguous() and x.dim() == 4
+    Cx, F, H, W = x.shape
+    Cy = 0
+    if y is not None:
+        _req(y, f32, "patchify.y")
+        assert y.is_contiguous() and y.shape[1:] == x.shape[1:]
+        Cy = y.shape[0]
+    out = torch.empty(F * (H // 2) * (W // 2), (Cx + Cy) * 4, dtype=bf16, device=x.device)
+    check(lib().prfl_patchify(_p(x), Cx, _p(y), Cy, _p(out), F, H, W, _stream()), "prfl_patchify")
+    return out
+
+
+def patchify_bwd(dpatches: torch.Tensor, Cx: int, F: int, H: int, W: int) -> torch.Tensor:
+    _req(dpatches, f32, "patchify_bwd.dp")
+    assert dpatches.is_contiguous()
+    Ct = dpatches.shape[1] // 4
+    dx = torch.empty(Cx, F, H, W, dtype=f32, device=dpatches.device)
+    check(lib().prfl_patchify_bwd(_p(dpatches), Cx, Ct, _p(dx), F, H, W, _stream()), "prfl_patchify_bwd")
+    return dx
+
+
+def unpatchify(tokens: torch.Tensor, c: int, grid: Tuple[int, int, int]) -> torch.Tensor:
+    """[F*h*w, 4c] fp32 -> [c, F, 2h, 2w] fp32 (model.py:683-705)."""
+    _req(tokens, f32, "unpatchify.tokens")
+    assert tokens.is_contiguous()
+    F, h, w = grid
+    assert tokens.shape[0] >= F * h * w and tokens.shape[1] == 4 * c
+    vid = torch.empty(c, F, 2 * h, 2 * w, dtype=f32, device=tokens.device)
+    check(lib().prfl_unpatchify(_p(tokens), _p(vid), c, F, h, w, 0, _stream()), "prfl_unpatchify")
+    return vid
+
+
+def unpatchify_bwd(dvid: torch.Tensor, rows: int) -> torch.Tensor:
+    _req(dvid, f32, "unpatchify_bwd.dvid")
+    assert dvid.is_contiguous()
+    c, F, H2, W2 = dvid.shape
+    tok = torch.zeros(rows, 4 * c, dtype=f32, device=dvid.device)
+    check(lib().prfl_unpatchify(_p(tok), _p(dvid), c, F, H2 // 2, W2 // 2, 1, _stream()), "prfl_unpatchify(inverse)")
+    return tok
+
+
+def sq_pool(x: torch.Tensor, wk_eff: torch.Tensor):
+    """Single-query attention pooling: x [L, C] fp32, wk_eff [8, C] fp32 -> pooled [8, C], (scores, stats)."""
+    _req(x, f32, "sq_pool.x")
+    _req(wk_eff, f32, "sq_pool.wk_eff")
+    assert x.is_contiguous() and wk_eff.is_contiguous() and x.dim() == 2
+    L, Cc = x.shape
+    NH = wk_eff.shape[0]
+    scores = torch.empty(L, NH, dtype=f32, device=x.device)
+    stats = torch.empty(2 * NH, dtype=f32, device=x.device)
+    pooled = torch.empty(NH, Cc, dtype=f32, device=x.device)
+    check(lib().prfl_sq_pool_fwd(_p(x), _p(wk_eff), _p(scores), _p(stats), _p(pooled), L, Cc, NH, _stream()), "prfl_sq_pool_fwd")
+    return pooled, scores, stats
+
+
+def sq_pool_bwd(x, wk_eff, scores, stats, pooled, dpooled, dx: Optional[torch.Tensor] = None, need_ds: bool = False):
+    L, Cc = x.shape
+    NH = wk_eff.shape[0]
+    acc = dx is not None
+    if dx is None:
+        dx = torch.empty_like(x)
+    ds = torch.empty(L, NH, dtype=f32, device=x.device) if need_ds else None
+    _req(dpooled, f32, "sq_pool_bwd.dpooled")
+    check(lib().prfl_sq_pool_bwd(_p(x), _p(wk_eff), _p(scores), _p(stats), _p(pooled), _p(dpooled.contiguous()), _p(dx), _p(ds),
+                                 L, Cc, NH, int(acc), _stream()), "prfl_sq_pool_bwd")
+    return dx, ds
+
+
+def a2a_pack(strided: torch.Tensor, packed: torch.Tensor, P: int, unpack: bool = False):
+    """strided: [L_loc, H, 128] bf16 view; packed: contiguous [P, L_loc, H/P, 128] bf16."""
+    _req(strided, bf16, "a2a.strided")
+    _req(packed, bf16, "a2a.packed")
+    L_loc, H, d = strided.shape
+    assert d == 128 and strided.stride(2) == 1 and packed.is_contiguous() and packed.numel() == strided.numel()
+    check(lib().prfl_a2a_pack(_p(strided), strided.stride(0), strided.stride(1), _p(packed), L_loc, H, P, int(unpack), _stream()),
+          "prfl_a2a_pack")
+    return strided if unpack else packed
