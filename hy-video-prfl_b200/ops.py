@@ -17,6 +17,38 @@ def _stream():
     return torch.cuda.current_stream().cuda_stream
 
 
+class KernelTimer:
+    """Optional CUDA-event timing of individual launches on the launching (current) stream; bench.py
+    switches it on for the timed region to get the dominant kernel's live duration for the roofline."""
+
+    def __init__(self, names):
+        self.names = set(names)
+        self.events = {n: [] for n in names}
+
+    def elapsed_ms(self, name):
+        return [a.elapsed_time(b) for a, b in self.events[name]]
+
+
+TIMER: Optional[KernelTimer] = None
+
+
+class _timed:
+    def __init__(self, name):
+        self.on = TIMER is not None and name in TIMER.names
+        self.name = name
+
+    def __enter__(self):
+        if self.on:
+            self.a = torch.cuda.Event(enable_timing=True)
+            self.b = torch.cuda.Event(enable_timing=True)
+            self.a.record()
+
+    def __exit__(self, *exc):
+        if self.on:
+            self.b.record()
+            TIMER.events[self.name].append((self.a, self.b))
+
+
 def _p(t: Optional[torch.Tensor]):
     return None if t is None else t.data_ptr()
 
@@ -97,8 +129,9 @@ def gemm(a: torch.Tensor, b: torch.Tensor, *, a_trans: bool = False, b_trans: bo
         _req(aux, bf16, "gemm.aux")
         assert aux.shape == (M, N) and aux.stride(1) == 1
         ldaux = aux.stride(0)
-    check(lib().prfl_gemm_bf16(_p(a), a.stride(0), int(a_trans), _p(b), b.stride(0), int(b_trans), _p(out), out.stride(0),
-                               _p(bias), _p(gate), _p(aux), ldaux, M, N, K, epi, int(beta), _stream()), "prfl_gemm_bf16")
+    with _timed("gemm"):
+        check(lib().prfl_gemm_bf16(_p(a), a.stride(0), int(a_trans), _p(b), b.stride(0), int(b_trans), _p(out), out.stride(0),
+                                   _p(bias), _p(gate), _p(aux), ldaux, M, N, K, epi, int(beta), _stream()), "prfl_gemm_bf16")
     return out
 
 
@@ -116,8 +149,9 @@ def attn_fwd(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, scale: Optional[
     lse = torch.empty(H, Lq, dtype=f32, device=q.device) if need_lse else None
     if scale is None:
         scale = 1.0 / math.sqrt(128)
-    check(lib().prfl_attn_fwd(_p(q), q.stride(0), q.stride(1), _p(k), k.stride(0), k.stride(1), _p(v), v.stride(0), v.stride(1),
-                              _p(out), out.stride(0), out.stride(1), _p(lse), Lq, Lk, H, float(scale), _stream()), "prfl_attn_fwd")
+    with _timed("attn_fwd_self" if Lk > 1024 else "attn_fwd_cross"):
+        check(lib().prfl_attn_fwd(_p(q), q.stride(0), q.stride(1), _p(k), k.stride(0), k.stride(1), _p(v), v.stride(0), v.stride(1),
+                                  _p(out), out.stride(0), out.stride(1), _p(lse), Lq, Lk, H, float(scale), _stream()), "prfl_attn_fwd")
     return (out, lse) if need_lse else out
 
 

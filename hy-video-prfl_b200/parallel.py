@@ -1,0 +1,181 @@
+"""Sequence-parallel (DeepSpeed-Ulysses) state and collectives with the reference's API
+(diffusers_lite/utils/parallel_states.py:10-74, diffusers_lite/utils/communication.py:17-20,40-160,224-273).
+
+Same names (`nccl_info`, `initialize_sequence_parallel_state`, `get_sequence_parallel_state`,
+`all_to_all_4D`, `all_gather`, `broadcast`), same tensor contracts.  Differences, all on purpose:
+  * payloads are bf16 (the reference ships q, k and the attention output as fp32);
+  * one staging copy per exchange (a CUDA kernel writing/reading the [P, L/P, H/P, 128] wire layout)
+    instead of reshape/transpose/contiguous on both sides;
+  * no torch.cuda.synchronize() after the collective (communication.py:80,113).
+The collective itself is NCCL `all_to_all_single` through torch.distributed (gloo on CPU in the tests).
+"""
+from __future__ import annotations
+
+import os
+from typing import Optional
+
+import torch
+import torch.distributed as dist
+
+
+class COMM_INFO:
+    def __init__(self):
+        self.group = None
+        self.sp_size = 1
+        self.global_rank = 0
+        self.rank_within_group = 0
+        self.group_id = 0
+
+
+nccl_info = COMM_INFO()
+_SEQUENCE_PARALLEL_STATE = False
+
+
+def initialize_sequence_parallel_state(sequence_parallel_size: int):
+    """parallel_states.py:34-44."""
+    global _SEQUENCE_PARALLEL_STATE
+    if sequence_parallel_size > 1:
+        _SEQUENCE_PARALLEL_STATE = True
+        initialize_sequence_parallel_group(sequence_parallel_size)
+    else:
+        _SEQUENCE_PARALLEL_STATE = False
+        nccl_info.group = None
+        nccl_info.sp_size = 1
+        nccl_info.global_rank = int(os.getenv("RANK", "0"))
+        nccl_info.rank_within_group = 0
+        nccl_info.group_id = int(os.getenv("RANK", "0"))
+
+
+def set_sequence_parallel_state(state: bool):
+    global _SEQUENCE_PARALLEL_STATE
+    _SEQUENCE_PARALLEL_STATE = state
+
+
+def get_sequence_parallel_state() -> bool:
+    return _SEQUENCE_PARALLEL_STATE
+
+
+def initialize_sequence_parallel_group(sequence_parallel_size: int):
+    """parallel_states.py:56-74: contiguous ranks form one SP group."""
+    rank = dist.get_rank() if dist.is_initialized() else int(os.getenv("RANK", "0"))
+    world_size = dist.get_world_size() if dist.is_initialized() else int(os.getenv("WORLD_SIZE", "1"))
+    assert world_size % sequence_parallel_size == 0, (
+        f"world_size must be divisible by sequence_parallel_size, but got world_size: {world_size}, "
+        f"sequence_parallel_size: {sequence_parallel_size}")
+    nccl_info.sp_size = sequence_parallel_size
+    nccl_info.global_rank = rank
+    for i in range(world_size // sequence_parallel_size):
+        ranks = range(i * sequence_parallel_size, (i + 1) * sequence_parallel_size)
+        group = dist.new_group(ranks)
+        if rank in ranks:
+            nccl_info.group = group
+            nccl_info.rank_within_group = rank - i * sequence_parallel_size
+            nccl_info.group_id = i
+
+
+def broadcast(input_: torch.Tensor):
+    """communication.py:17-19."""
+    src = nccl_info.group_id * nccl_info.sp_size
+    dist.broadcast(input_, src=src, group=nccl_info.group)
+
+
+# ------------------------------------------------------------------------------------------------
+# layout algebra shared by the CUDA path and the CPU (gloo) tests
+# ------------------------------------------------------------------------------------------------
+def _pack_heads(x: torch.Tensor, P: int) -> torch.Tensor:
+    """[L_loc, H, d] -> wire layout [P, L_loc, H/P, d]  (destination rank major)."""
+    L, H, d = x.shape
+    if x.is_cuda:
+        from . import ops
+        packed = torch.empty(P, L, H // P, d, dtype=x.dtype, device=x.device)
+        return ops.a2a_pack(x, packed, P)
+    return x.reshape(L, P, H // P, d).permute(1, 0, 2, 3).contiguous()
+
+
+def _unpack_heads(packed: torch.Tensor, P: int) -> torch.Tensor:
+    """wire layout [P, L_loc, H/P, d] (source rank major) -> [L_loc, H, d]."""
+    _, L, Hl, d = packed.shape
+    if packed.is_cuda:
+        from . import ops
+        out = torch.empty(L, P * Hl, d, dtype=packed.dtype, device=packed.device)
+        return ops.a2a_pack(out, packed, P, unpack=True)
+    return packed.permute(1, 0, 2, 3).reshape(L, P * Hl, d).contiguous()
+
+
+def _a2a(buf: torch.Tensor) -> torch.Tensor:
+    out = torch.empty_like(buf)
+    dist.all_to_all_single(out, buf, group=nccl_info.group)
+    return out
+
+
+def ulysses_scatter_tokens(x: torch.Tensor, P: int) -> torch.Tensor:
+    """scatter heads / gather tokens: local [L/P, H, d] -> [L, H/P, d] (communication.py:60-89).
+    The receive buffer [P, L/P, H/P, d] already is [L, H/P, d] in global token order."""
+    L, H, d = x.shape
+    return _a2a(_pack_heads(x, P)).view(P * L, H // P, d)
+
+
+def ulysses_gather_tokens(x: torch.Tensor, P: int) -> torch.Tensor:
+    """scatter tokens / gather heads: [L, H/P, d] -> local [L/P, H, d] (communication.py:91-123).
+    The send buffer is x itself ([P, L/P, H/P, d] by token chunk)."""
+    L, Hl, d = x.shape
+    recv = _a2a(x.contiguous().view(P, L // P, Hl, d))
+    return _unpack_heads(recv, P)
+
+
+class SeqAllToAll4D(torch.autograd.Function):
+    """communication.py:128-152: backward = the exchange with scatter/gather swapped."""
+
+    @staticmethod
+    def forward(ctx, group, input_, scatter_idx, gather_idx):
+        ctx.scatter_idx, ctx.gather_idx = scatter_idx, gather_idx
+        return _all_to_all_4D(input_, scatter_idx, gather_idx)
+
+    @staticmethod
+    def backward(ctx, grad_output):
+        return None, _all_to_all_4D(grad_output, ctx.gather_idx, ctx.scatter_idx), None, None
+
+
+def _all_to_all_4D(input_: torch.Tensor, scatter_idx: int, gather_idx: int) -> torch.Tensor:
+    assert input_.dim() == 4, f"input must be 4D tensor, got {input_.dim()} and shape {input_.shape}"
+    P = nccl_info.sp_size
+    if scatter_idx == 2 and gather_idx == 1:
+        return torch.stack([ulysses_scatter_tokens(input_[b], P) for b in range(input_.shape[0])])
+    if scatter_idx == 1 and gather_idx == 2:
+        return torch.stack([ulysses_gather_tokens(input_[b], P) for b in range(input_.shape[0])])
+    raise RuntimeError("scatter_idx must be 1 or 2 and gather_idx must be 1 or 2")
+
+
+def all_to_all_4D(input_: torch.Tensor, scatter_dim: int = 2, gather_dim: int = 1):
+    """communication.py:155-160.  [b, L/P, H, d] <-> [b, L, H/P, d]."""
+    return SeqAllToAll4D.apply(nccl_info.group, input_, scatter_dim, gather_dim)
+
+
+class _AllGather(torch.autograd.Function):
+    """communication.py:224-260: forward all_gather + cat, backward = own slice (no reduction)."""
+
+    @staticmethod
+    def forward(ctx, input_, dim):
+        ctx.dim = dim
+        ctx.input_size = input_.size(dim)
+        world = nccl_info.sp_size
+        input_ = input_.contiguous()
+        if dim == 0 or all(s == 1 for s in input_.shape[:dim]):
+            out = torch.empty((world,) + tuple(input_.shape), dtype=input_.dtype, device=input_.device)
+            dist.all_gather_into_tensor(out.view(-1), input_.view(-1), group=nccl_info.group)
+            shp = list(input_.shape)
+            shp[dim] *= world
+            return out.reshape(shp)     # leading dims are all 1 => the rank-major buffer IS the concatenation
+        parts = [torch.empty_like(input_) for _ in range(world)]
+        dist.all_gather(parts, input_, group=nccl_info.group)
+        return torch.cat(parts, dim=dim)
+
+    @staticmethod
+    def backward(ctx, grad_output):
+        rank = nccl_info.rank_within_group
+        return grad_output.narrow(ctx.dim, rank * ctx.input_size, ctx.input_size).contiguous(), None
+
+
+def all_gather(input_: torch.Tensor, dim: int = 1):
+    """communication.py:263-273."""
+    return _AllGather.apply(input_, dim)
