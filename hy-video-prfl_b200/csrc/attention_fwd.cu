@@ -171,18 +171,22 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       for (int c = 0; c < 4; ++c) tmem_ld32(s_addr + c * 32, r[c]);
       tmem_wait_ld();
       const int valid = p.Lk - j * KT;  // columns >= valid are padding (TMA zero fill)
-      float mx = -INFINITY;
+      if (valid < KT) {                 // tail tile only (warp-uniform)
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            if (c * 32 + i >= valid) r[c][i] = 0xff800000u;  // -inf
+      }
+      float mx0 = -INFINITY, mx1 = -INFINITY;
 #pragma unroll
       for (int c = 0; c < 4; ++c)
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          float v = __uint_as_float(r[c][i]);
-          if (valid < KT && c * 32 + i >= valid) {
-            v = -INFINITY;
-            r[c][i] = __float_as_uint(v);
-          }
-          mx = fmaxf(mx, v);
+        for (int i = 0; i < 32; i += 4) {
+          mx0 = fmax3(mx0, __uint_as_float(r[c][i]), __uint_as_float(r[c][i + 1]));
+          mx1 = fmax3(mx1, __uint_as_float(r[c][i + 2]), __uint_as_float(r[c][i + 3]));
         }
+      const float mx = fmaxf(mx0, mx1);
       const float m_new = fmaxf(m_used, mx * p.scale_log2);
       if (j == 0) {
         m_used = m_new;
@@ -201,22 +205,26 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
           tmem_st32(o_addr + c * 32, o);
         }
       }
-      const float neg_m = -m_used;
+      const float2 neg_m2 = make_float2(-m_used, -m_used);
+      const float2 sc2 = make_float2(p.scale_log2, p.scale_log2);
+      float2 acc0 = make_float2(0.f, 0.f), acc1 = make_float2(0.f, 0.f);
 #pragma unroll
       for (int c = 0; c < 4; c += 2) {
         uint32_t pk[32];
 #pragma unroll
         for (int i = 0; i < 32; i += 2) {
-          float a0 = fast_exp2(fmaf(__uint_as_float(r[c][i]), p.scale_log2, neg_m));
-          float a1 = fast_exp2(fmaf(__uint_as_float(r[c][i + 1]), p.scale_log2, neg_m));
-          float b0 = fast_exp2(fmaf(__uint_as_float(r[c + 1][i]), p.scale_log2, neg_m));
-          float b1 = fast_exp2(fmaf(__uint_as_float(r[c + 1][i + 1]), p.scale_log2, neg_m));
-          l_sum += (a0 + a1) + (b0 + b1);
-          pk[i >> 1] = pack_bf16x2(a0, a1);
-          pk[16 + (i >> 1)] = pack_bf16x2(b0, b1);
+          float2 xa = ffma2(make_float2(__uint_as_float(r[c][i]), __uint_as_float(r[c][i + 1])), sc2, neg_m2);
+          float2 xb = ffma2(make_float2(__uint_as_float(r[c + 1][i]), __uint_as_float(r[c + 1][i + 1])), sc2, neg_m2);
+          float2 pa = make_float2(fast_exp2(xa.x), fast_exp2(xa.y));
+          float2 pb = make_float2(fast_exp2(xb.x), fast_exp2(xb.y));
+          acc0 = fadd2(acc0, pa);
+          acc1 = fadd2(acc1, pb);
+          pk[i >> 1] = pack_bf16x2(pa.x, pa.y);
+          pk[16 + (i >> 1)] = pack_bf16x2(pb.x, pb.y);
         }
         tmem_st32(s_addr + c * 16, pk);  // P columns [32*(c/2), +32) hold keys [64*(c/2), +64)
       }
+      l_sum += (acc0.x + acc0.y) + (acc1.x + acc1.y);
       tmem_wait_st();
       tc_fence_before();
       __syncwarp();

@@ -22,7 +22,7 @@ struct GemmParams {
   int64_t ldc;
   const float* bias;
   const float* gate;
-  const __nv_bfloat16* aux;
+  __nv_bfloat16* aux;   // DGELU: input (pre-activation); GELU / RESIDUAL: optional output bf16(acc + bias)
   int64_t ldaux;
   int M, N, K, epi, beta;
   int tiles_m, tiles_n, num_kb;
@@ -168,6 +168,18 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         if (p.epi == PRFL_EPI_BF16 || p.epi == PRFL_EPI_BF16_GELU || p.epi == PRFL_EPI_BF16_DGELU) {
           __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + (int64_t)row * p.ldc + col0;
           if (p.epi == PRFL_EPI_BF16_GELU) {
+            if (p.aux) {
+              __nv_bfloat16* ax = p.aux + (int64_t)row * p.ldaux + col0;
+#pragma unroll
+              for (int j = 0; j < 32; j += 8) {
+                if (col0 + j < p.N) {
+                  uint4 o4;
+                  o4.x = pack_bf16x2(v[j], v[j + 1]); o4.y = pack_bf16x2(v[j + 2], v[j + 3]);
+                  o4.z = pack_bf16x2(v[j + 4], v[j + 5]); o4.w = pack_bf16x2(v[j + 6], v[j + 7]);
+                  *reinterpret_cast<uint4*>(ax + j) = o4;
+                }
+              }
+            }
 #pragma unroll
             for (int j = 0; j < 32; ++j) v[j] = gelu_tanh(bf16_round(v[j]));
           } else if (p.epi == PRFL_EPI_BF16_DGELU) {
@@ -197,6 +209,18 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         } else {
           float* o = reinterpret_cast<float*>(p.out) + (int64_t)row * p.ldc + col0;
           if (p.epi == PRFL_EPI_RESIDUAL) {
+            if (p.aux) {
+              __nv_bfloat16* ax = p.aux + (int64_t)row * p.ldaux + col0;
+#pragma unroll
+              for (int j = 0; j < 32; j += 8) {
+                if (col0 + j < p.N) {
+                  uint4 o4;
+                  o4.x = pack_bf16x2(v[j], v[j + 1]); o4.y = pack_bf16x2(v[j + 2], v[j + 3]);
+                  o4.z = pack_bf16x2(v[j + 4], v[j + 5]); o4.w = pack_bf16x2(v[j + 6], v[j + 7]);
+                  *reinterpret_cast<uint4*>(ax + j) = o4;
+                }
+              }
+            }
 #pragma unroll
             for (int j = 0; j < 32; j += 4) {
               if (col0 + j < p.N) {
@@ -260,7 +284,7 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const Gem
 using namespace prfl;
 
 extern "C" int prfl_gemm_bf16(const void* A, int64_t lda, int a_trans, const void* B, int64_t ldb, int b_trans, void* out,
-                              int64_t ldc, const float* bias, const float* gate, const void* aux_bf16, int64_t ldaux, int M,
+                              int64_t ldc, const float* bias, const float* gate, void* aux_bf16, int64_t ldaux, int M,
                               int N, int K, int epi, int beta, prfl_stream_t stream) {
   PRFL_CHECK_ARCH();
   PRFL_REQUIRE(M > 0 && N > 0 && K > 0 && K % 8 == 0 && N % 8 == 0, PRFL_E_SHAPE, "gemm: M=%d N=%d K=%d (need K%%8==0, N%%8==0)", M, N, K);
@@ -268,7 +292,8 @@ extern "C" int prfl_gemm_bf16(const void* A, int64_t lda, int a_trans, const voi
   PRFL_REQUIRE(!(a_trans && M % 8 != 0), PRFL_E_SHAPE, "gemm: transposed A needs M%%8==0 (M=%d)", M);
   PRFL_REQUIRE(lda % 8 == 0 && ldb % 8 == 0 && ldc % 4 == 0 && lda >= (a_trans ? M : K) && ldb >= (b_trans ? N : K) && ldc >= N,
                PRFL_E_ALIGN, "gemm: leading dims lda=%lld ldb=%lld ldc=%lld", (long long)lda, (long long)ldb, (long long)ldc);
-  PRFL_REQUIRE(epi != PRFL_EPI_BF16_DGELU || (aux_bf16 && ldaux >= N && ldaux % 8 == 0), PRFL_E_SHAPE, "gemm: DGELU needs aux");
+  PRFL_REQUIRE(epi != PRFL_EPI_BF16_DGELU || aux_bf16, PRFL_E_SHAPE, "gemm: DGELU needs aux");
+  PRFL_REQUIRE(!aux_bf16 || (ldaux >= N && ldaux % 8 == 0), PRFL_E_ALIGN, "gemm: ldaux=%lld", (long long)ldaux);
   PRFL_REQUIRE((reinterpret_cast<uintptr_t>(out) & 15) == 0 && (reinterpret_cast<uintptr_t>(bias) & 15) == 0 &&
                    (reinterpret_cast<uintptr_t>(gate) & 15) == 0 && (reinterpret_cast<uintptr_t>(aux_bf16) & 15) == 0 &&
                    ((epi == PRFL_EPI_F32 || epi == PRFL_EPI_RESIDUAL) ? true : ldc % 8 == 0),
@@ -282,7 +307,7 @@ extern "C" int prfl_gemm_bf16(const void* A, int64_t lda, int a_trans, const voi
   else rc = make_tmap_2d(&tmB, B, (uint64_t)N, (uint64_t)K, (uint64_t)ldb * 2, 64, 64, 1);
   if (rc != PRFL_OK) return rc;
   GemmParams p;
-  p.out = out; p.ldc = ldc; p.bias = bias; p.gate = gate; p.aux = (const __nv_bfloat16*)aux_bf16; p.ldaux = ldaux;
+  p.out = out; p.ldc = ldc; p.bias = bias; p.gate = gate; p.aux = (__nv_bfloat16*)aux_bf16; p.ldaux = ldaux;
   p.M = M; p.N = N; p.K = K; p.epi = epi; p.beta = beta;
   p.tiles_m = (M + BM - 1) / BM; p.tiles_n = (N + BN - 1) / BN; p.num_kb = (K + BK - 1) / BK;
   cudaStream_t st = (cudaStream_t)stream;

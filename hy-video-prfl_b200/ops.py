@@ -125,7 +125,7 @@ def gemm(a: torch.Tensor, b: torch.Tensor, *, a_trans: bool = False, b_trans: bo
         _req(gate, f32, "gemm.gate")
         assert gate.numel() == N
     ldaux = 0
-    if aux is not None:
+    if aux is not None:          # input for DGELU; extra output (pre-activation / un-gated branch) for GELU / RESIDUAL
         _req(aux, bf16, "gemm.aux")
         assert aux.shape == (M, N) and aux.stride(1) == 1
         ldaux = aux.stride(0)
@@ -153,6 +153,91 @@ def attn_fwd(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, scale: Optional[
         check(lib().prfl_attn_fwd(_p(q), q.stride(0), q.stride(1), _p(k), k.stride(0), k.stride(1), _p(v), v.stride(0), v.stride(1),
                                   _p(out), out.stride(0), out.stride(1), _p(lse), Lq, Lk, H, float(scale), _stream()), "prfl_attn_fwd")
     return (out, lse) if need_lse else out
+
+
+def attn_bwd(q, k, v, o, dout, lse, dq=None, dk=None, dv=None, scale: Optional[float] = None):
+    """Gradients of attn_fwd.  All tensors [L, H, 128] bf16 views (last stride 1); lse [H, Lq] fp32 from the forward."""
+    for t, n in ((q, "q"), (k, "k"), (v, "v"), (o, "o"), (dout, "dout")):
+        _req(t, bf16, "attn_bwd." + n)
+        assert t.dim() == 3 and t.shape[2] == 128 and t.stride(2) == 1, (n, t.shape, t.stride())
+    Lq, H, _ = q.shape
+    Lk = k.shape[0]
+    dq = torch.empty(Lq, H, 128, dtype=bf16, device=q.device) if dq is None else dq
+    dk = torch.empty(Lk, H, 128, dtype=bf16, device=q.device) if dk is None else dk
+    dv = torch.empty(Lk, H, 128, dtype=bf16, device=q.device) if dv is None else dv
+    delta = torch.empty(H, Lq, dtype=f32, device=q.device)
+    _req(lse, f32, "attn_bwd.lse")
+    assert lse.shape == (H, Lq) and lse.is_contiguous()
+    if scale is None:
+        scale = 1.0 / math.sqrt(128)
+    args = []
+    for t in (q, k, v, o, dout):
+        args += [_p(t), t.stride(0), t.stride(1)]
+    args += [_p(lse), _p(delta)]
+    for t in (dq, dk, dv):
+        assert t.dtype == bf16 and t.stride(2) == 1
+        args += [_p(t), t.stride(0), t.stride(1)]
+    with _timed("attn_bwd_self" if Lk > 1024 else "attn_bwd_cross"):
+        check(lib().prfl_attn_bwd(*args, Lq, Lk, H, float(scale), _stream()), "prfl_attn_bwd")
+    return dq, dk, dv
+
+
+def colsum_parts(rows: int) -> int:
+    return (rows + 255) // 256
+
+
+def ln_mod_bwd(x, dy, scale, gamma, mean, rstd, dx_accum, need_param_grads: bool):
+    """dx_accum += dL/dx; returns (sum dy, sum dy*xhat) as [C] fp32 (or (None, None))."""
+    _req(x, f32, "ln_mod_bwd.x")
+    _req(dy, bf16, "ln_mod_bwd.dy")
+    _req(dx_accum, f32, "ln_mod_bwd.dx")
+    assert x.is_contiguous() and dy.is_contiguous() and dx_accum.is_contiguous()
+    rows, C = x.shape
+    p1 = p2 = None
+    if need_param_grads:
+        p1 = torch.empty(colsum_parts(rows), C, dtype=f32, device=x.device)
+        p2 = torch.empty_like(p1)
+    check(lib().prfl_ln_mod_bwd(_p(x), _p(dy), _p(scale), _p(gamma), _p(mean), _p(rstd), _p(dx_accum), _p(p1), _p(p2), rows, C,
+                                _stream()), "prfl_ln_mod_bwd")
+    if need_param_grads:
+        return p1.sum(0), p2.sum(0)
+    return None, None
+
+
+def rmsnorm_rope_bwd_(x, w, cos, sin, dy, rstd, n_rot: int = 0, pos0: int = 0, need_dw: bool = True):
+    """dy (bf16 [rows, C] view) is overwritten with dL/dx; returns dL/dw [C] fp32 (or None)."""
+    _req(x, bf16, "rmsnorm_rope_bwd.x")
+    _req(dy, bf16, "rmsnorm_rope_bwd.dy")
+    rows, C = x.shape
+    gw = torch.empty(rows, C, dtype=bf16, device=x.device) if need_dw else None
+    check(lib().prfl_rmsnorm_rope_bwd(_p(x), x.stride(0), _p(w), _p(cos), _p(sin), _p(dy), dy.stride(0), _p(rstd), _p(dy),
+                                      dy.stride(0), _p(gw), C if need_dw else 0, rows, C, int(n_rot), int(pos0), _stream()),
+          "prfl_rmsnorm_rope_bwd")
+    return colsum(gw) if need_dw else None
+
+
+def colsum(a: torch.Tensor) -> torch.Tensor:
+    """Column sums of a bf16 [rows, N] view (row stride free) -> [N] fp32."""
+    _req(a, bf16, "colsum.a")
+    assert a.dim() == 2 and a.stride(1) == 1
+    rows, N = a.shape
+    part = torch.empty(colsum_parts(rows), N, dtype=f32, device=a.device)
+    check(lib().prfl_colsum_bf16(_p(a), a.stride(0), _p(part), rows, N, _stream()), "prfl_colsum_bf16")
+    return part.sum(0)
+
+
+def gate_bwd(dx: torch.Tensor, y: Optional[torch.Tensor], gate: Optional[torch.Tensor]):
+    """dy = bf16(dx * gate) and dgate = sum_rows dx * y (None if y is None)."""
+    _req(dx, f32, "gate_bwd.dx")
+    assert dx.is_contiguous() and dx.dim() == 2
+    rows, N = dx.shape
+    dy = torch.empty(rows, N, dtype=bf16, device=dx.device)
+    part = torch.empty(colsum_parts(rows), N, dtype=f32, device=dx.device) if y is not None else None
+    if y is not None:
+        _req(y, bf16, "gate_bwd.y")
+        assert y.is_contiguous()
+    check(lib().prfl_gate_bwd(_p(dx), _p(y), _p(gate), _p(dy), _p(part), rows, N, _stream()), "prfl_gate_bwd")
+    return dy, (part.sum(0) if part is not None else None)
 
 
 def cast_bf16(src: torch.Tensor) -> torch.Tensor:

@@ -63,6 +63,29 @@ int prfl_ln_mod_fwd(const float* x, const float* shift, const float* scale, cons
 int prfl_rmsnorm_rope_fwd(const void* x_bf16, int64_t ldx, const float* w, const float* cos_tab, const float* sin_tab,
                           void* out_bf16, int64_t ldo, float* rstd, int64_t rows, int C, int64_t n_rot, int64_t pos0,
                           float eps, prfl_stream_t stream);
+/* ---- backward of the two norm kernels + the token-dimension reductions ---------------------------
+ * Replace what autograd derives for model.py:345,352,353 (LayerNorm + modulate / affine), model.py:106-122 + 60-103
+ * (RMSNorm + RoPE) and the bias / modulation / gate / norm-weight gradient reductions over tokens.
+ * Column reductions write PARTIAL sums [nparts, N] f32 (nparts = prfl_colsum_parts(rows), 256 rows each); the caller
+ * adds the nparts rows (N floats each — negligible). */
+int prfl_colsum_parts(int64_t rows);
+/* dx_accum[rows, C] (f32) += dL/dx of prfl_ln_mod_fwd given dy (bf16).  If dshift_part/dscale_part are given they
+ * receive partial sums of dy and dy * xhat: (dshift, dscale) of the modulated form, (dbeta, dgamma) of the affine form. */
+int prfl_ln_mod_bwd(const float* x, const void* dy_bf16, const float* scale, const float* gamma, const float* mean,
+                    const float* rstd, float* dx_accum, float* dshift_part, float* dscale_part, int64_t rows, int C,
+                    prfl_stream_t stream);
+/* dx (bf16, may alias dy) = dL/dx of prfl_rmsnorm_rope_fwd; gw_bf16 [rows, C] (or NULL) = dt * bf16(x * rstd), whose
+ * column sum (prfl_colsum_bf16) is dL/dw. */
+int prfl_rmsnorm_rope_bwd(const void* x_bf16, int64_t ldx, const float* w, const float* cos_tab, const float* sin_tab,
+                          const void* dy_bf16, int64_t lddy, const float* rstd, void* dx_bf16, int64_t lddx, void* gw_bf16,
+                          int64_t ldgw, int64_t rows, int C, int64_t n_rot, int64_t pos0, prfl_stream_t stream);
+/* part[chunk, n] = sum over the chunk's rows of a[row, n] (bias and norm-weight gradients). */
+int prfl_colsum_bf16(const void* a_bf16, int64_t lda, float* part, int64_t rows, int N, prfl_stream_t stream);
+/* Backward of x_out = x_in + gate * y (model.py:348,355): dy_bf16 = bf16(dx * gate) (gate NULL => 1, i.e. a cast);
+ * dgate_part (or NULL) = partial sums of dx * y. */
+int prfl_gate_bwd(const float* dx, const void* y_bf16, const float* gate, void* dy_bf16, float* dgate_part, int64_t rows, int N,
+                  prfl_stream_t stream);
+
 /* ---- bf16 tcgen05 GEMM with fused epilogues ---------------------------------------------------
  * Replaces cuBLAS(Lt) behind nn.Linear on the path: q,k,v,o (model.py:156-159,175-177,200),
  * cross-attn q,k,v,o (model.py:216-225, 256-270), FFN (model.py:313-315), patch embedding as a
@@ -77,7 +100,9 @@ int prfl_rmsnorm_rope_fwd(const void* x_bf16, int64_t ldx, const float* w, const
  *   PRFL_EPI_F32        out_f32[m,n]   = acc + bias[n]        (beta=1: out_f32 += ...; wgrad accumulation)
  *   PRFL_EPI_RESIDUAL   out_f32[m,n]  += gate[n] * bf16(acc + bias[n])   gate NULL => 1
  *                       (fuses the gated residual adds model.py:348,352,355 into o / ffn.2)
- *   PRFL_EPI_BF16_DGELU out_bf16[m,n]  = bf16(acc * gelu_tanh'(aux_bf16[m,n]))   (FFN backward)
+ *   PRFL_EPI_BF16_DGELU out_bf16[m,n]  = bf16(acc * gelu_tanh'(aux_bf16[m,n]))   (FFN backward; aux is an INPUT)
+ * With PRFL_EPI_BF16_GELU or PRFL_EPI_RESIDUAL a non-NULL aux_bf16 [M, N] (ldaux) is an extra OUTPUT that receives
+ * bf16(acc + bias[n]) — the pre-activation / the un-gated branch output the backward needs.
  * bias: [N] f32 or NULL.  M,N,K > 0; K % 8 == 0; N % 8 == 0; lda/ldb/ldc % 8 == 0. */
 #define PRFL_EPI_BF16 0
 #define PRFL_EPI_BF16_GELU 1
@@ -85,7 +110,7 @@ int prfl_rmsnorm_rope_fwd(const void* x_bf16, int64_t ldx, const float* w, const
 #define PRFL_EPI_RESIDUAL 3
 #define PRFL_EPI_BF16_DGELU 4
 int prfl_gemm_bf16(const void* A, int64_t lda, int a_trans, const void* B, int64_t ldb, int b_trans, void* out,
-                   int64_t ldc, const float* bias, const float* gate, const void* aux_bf16, int64_t ldaux, int M, int N,
+                   int64_t ldc, const float* bias, const float* gate, void* aux_bf16, int64_t ldaux, int M, int N,
                    int K, int epi, int beta, prfl_stream_t stream);
 
 /* ---- flash attention, bf16, head_dim 128, non-causal ------------------------------------------
@@ -99,6 +124,16 @@ int prfl_gemm_bf16(const void* A, int64_t lda, int a_trans, const void* B, int64
 int prfl_attn_fwd(const void* q, int64_t q_ld_tok, int64_t q_ld_head, const void* k, int64_t k_ld_tok,
                   int64_t k_ld_head, const void* v, int64_t v_ld_tok, int64_t v_ld_head, void* o, int64_t o_ld_tok,
                   int64_t o_ld_head, float* lse, int Lq, int Lk, int H, float scale, prfl_stream_t stream);
+/* Backward (replaces flash_attn's bwd kernels reached through autograd from the same call sites): dq, dk, dv (bf16,
+ * same addressing as q/k/v) from q, k, v, o, dout and the forward's lse.  delta: [H, Lq] f32 workspace, filled here
+ * with rowsum(dout * o).  Two tcgen05 kernels (dK/dV with keys resident, dQ with queries resident); no atomics. */
+int prfl_attn_bwd(const void* q, int64_t q_ld_tok, int64_t q_ld_head, const void* k, int64_t k_ld_tok,
+                  int64_t k_ld_head, const void* v, int64_t v_ld_tok, int64_t v_ld_head, const void* o,
+                  int64_t o_ld_tok, int64_t o_ld_head, const void* dout, int64_t do_ld_tok, int64_t do_ld_head,
+                  const float* lse, float* delta, void* dq, int64_t dq_ld_tok, int64_t dq_ld_head, void* dk,
+                  int64_t dk_ld_tok, int64_t dk_ld_head, void* dv, int64_t dv_ld_tok, int64_t dv_ld_head, int Lq, int Lk,
+                  int H, float scale, prfl_stream_t stream);
+
 /* ---- patchify / unpatchify -------------------------------------------------------------------
  * Patch embedding Conv3d(kernel = stride = (1,2,2)) (model.py:497-498,578-581) = gather + GEMM:
  * this gathers latent [Cin, F, H, W] f32 into patches [F*(H/2)*(W/2), Cin*4] bf16, column index

@@ -209,3 +209,112 @@ def test_sq_pool(ops, L, C):
     dx, ds = ops.sq_pool_bwd(x, wk, scores, stats, pooled, dpooled, need_ds=True)
     torch.testing.assert_close(dx, xr.grad, rtol=1e-3, atol=1e-4)
     torch.testing.assert_close(ds.t() @ x, wr.grad, rtol=1e-3, atol=1e-4)
+
+
+# ---------------------------------------------------------------------------------------------
+# backward kernels
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("Lq,Lk,H", [(128, 128, 1), (256, 192, 2), (300, 300, 2), (1950, 1950, 2), (300, 512, 2), (700, 769, 1)])
+def test_attn_bwd(ops, Lq, Lk, H):
+    q = _rand(Lq, H, 128, dtype=torch.bfloat16, seed=70)
+    k = _rand(Lk, H, 128, dtype=torch.bfloat16, seed=71)
+    v = _rand(Lk, H, 128, dtype=torch.bfloat16, seed=72)
+    do = _rand(Lq, H, 128, dtype=torch.bfloat16, seed=73)
+    o, lse = ops.attn_fwd(q, k, v, need_lse=True)
+    dq, dk, dv = ops.attn_bwd(q, k, v, o, do, lse)
+    qf, kf, vf = (t.float().requires_grad_(True) for t in (q, k, v))
+    ref, _ = _attn_ref(qf, kf, vf, 1 / math.sqrt(128))
+    ref.backward(do.float())
+    for name, a, b in (("dq", dq, qf.grad), ("dk", dk, kf.grad), ("dv", dv, vf.grad)):
+        cos, rel = cos_rel(a, b)
+        assert cos > 0.9995 and rel < 2e-2, (name, cos, rel)     # bf16 P / dS operands, bf16 outputs
+
+
+@pytest.mark.parametrize("C,rows", [(256, 300), (1536, 515), (5120, 300)])
+@pytest.mark.parametrize("variant", ["mod", "affine", "plain"])
+def test_ln_mod_bwd(ops, C, rows, variant):
+    x = _rand(rows, C, seed=80) * 2 + 0.3
+    dy = _rand(rows, C, dtype=torch.bfloat16, seed=81)
+    shift = scale = gamma = beta = None
+    if variant == "mod":
+        shift, scale = _rand(C, seed=82), _rand(C, seed=83) * 0.3
+    if variant == "affine":
+        gamma, beta = 1 + 0.1 * _rand(C, seed=84), 0.1 * _rand(C, seed=85)
+    _, mean, rstd = ops.ln_mod(x, shift, scale, gamma, beta, 1e-6, save_stats=True)
+    dx0 = _rand(rows, C, seed=86)
+    dx = dx0.clone()
+    g1, g2 = ops.ln_mod_bwd(x, dy, scale, gamma, mean, rstd, dx, need_param_grads=(variant != "plain"))
+    xr = x.clone().requires_grad_(True)
+    leaves = [t.clone().requires_grad_(True) if t is not None else None for t in (shift, scale, gamma, beta)]
+    y = torch.nn.functional.layer_norm(xr, (C,), leaves[2], leaves[3], 1e-6)
+    if variant == "mod":
+        y = y * (1 + leaves[1]) + leaves[0]
+    y.backward(dy.float())
+    torch.testing.assert_close(dx - dx0, xr.grad, rtol=2e-3, atol=2e-3)
+    if variant == "mod":
+        torch.testing.assert_close(g1, leaves[0].grad, rtol=2e-3, atol=5e-2)
+        torch.testing.assert_close(g2, leaves[1].grad, rtol=2e-3, atol=5e-2)
+    if variant == "affine":
+        torch.testing.assert_close(g1, leaves[3].grad, rtol=2e-3, atol=5e-2)
+        torch.testing.assert_close(g2, leaves[2].grad, rtol=2e-3, atol=5e-2)
+
+
+@pytest.mark.parametrize("C,rows", [(256, 40), (1536, 300), (5120, 130)])
+@pytest.mark.parametrize("rope", [False, True])
+def test_rmsnorm_rope_bwd(ops, C, rows, rope):
+    from prfl_b200.rope import rope_tables
+    H = C // 128
+    x = _rand(rows, C, dtype=torch.bfloat16, seed=90)
+    w = 1 + 0.1 * _rand(C, seed=91)
+    dy = _rand(rows, C, dtype=torch.bfloat16, seed=92)
+    n_rot, pos0 = (rows - 2, 3) if rope else (0, 0)
+    cos = sin = None
+    if rope:
+        cos, sin = rope_tables((2, 5, (rows + 9) // 10 + 1), torch.device("cuda"))
+    _, rstd = ops.rmsnorm_rope_(x.clone(), w, cos, sin, 1e-6, n_rot, pos0, save_rstd=True)
+    xr = x.float().requires_grad_(True)
+    wr = w.clone().requires_grad_(True)
+    t = xr * torch.rsqrt(xr.pow(2).mean(-1, keepdim=True) + 1e-6) * wr
+    if rope:
+        c, s = cos[pos0:pos0 + n_rot, None, :], sin[pos0:pos0 + n_rot, None, :]
+        r = t[:n_rot].view(n_rot, H, 64, 2)
+        rot = torch.stack([r[..., 0] * c - r[..., 1] * s, r[..., 0] * s + r[..., 1] * c], -1).view(n_rot, C)
+        t = torch.cat([rot, t[n_rot:]])
+    t.backward(dy.float())
+    g = dy.clone()
+    dw = ops.rmsnorm_rope_bwd_(x, w, cos, sin, g, rstd, n_rot, pos0)
+    cosv, rel = cos_rel(g, xr.grad)
+    assert cosv > 0.9999 and rel < 1.5e-2, (cosv, rel)
+    cosv, rel = cos_rel(dw, wr.grad)
+    assert cosv > 0.9999 and rel < 1.5e-2, (cosv, rel)
+
+
+def test_colsum_gate_bwd(ops):
+    rows, N = 1000, 1536
+    a = _rand(rows, 2 * N, dtype=torch.bfloat16, seed=95)[:, N:]
+    torch.testing.assert_close(ops.colsum(a), a.float().sum(0), rtol=1e-4, atol=1e-3)
+    dx, y, gate = _rand(rows, N, seed=96), _rand(rows, N, dtype=torch.bfloat16, seed=97), _rand(N, seed=98)
+    dy, dg = ops.gate_bwd(dx, y, gate)
+    torch.testing.assert_close(dy.float(), dx * gate, rtol=1e-2, atol=1e-2)
+    torch.testing.assert_close(dg, (dx * y.float()).sum(0), rtol=1e-4, atol=1e-3)
+    dy, dg = ops.gate_bwd(dx, None, None)
+    assert dg is None and torch.equal(dy, dx.bfloat16())
+
+
+def test_gemm_aux_outputs(ops):
+    M, N, K = 300, 512, 256
+    a = _rand(M, K, dtype=torch.bfloat16, seed=100, scale=0.5)
+    b = _rand(N, K, dtype=torch.bfloat16, seed=101, scale=0.2)
+    bias = _rand(N, seed=102)
+    acc = a.float() @ b.float().t() + bias
+    pre = torch.empty(M, N, dtype=torch.bfloat16, device="cuda")
+    out = ops.gemm(a, b, bias=bias, epi=ops.EPI_BF16_GELU, aux=pre)
+    torch.testing.assert_close(pre.float(), acc, rtol=1e-2, atol=1e-2)
+    torch.testing.assert_close(out.float(), torch.nn.functional.gelu(pre.float(), approximate="tanh"), rtol=1.6e-2, atol=1.6e-2)
+    x0 = _rand(M, N, seed=103)
+    x = x0.clone()
+    y = torch.empty(M, N, dtype=torch.bfloat16, device="cuda")
+    gate = _rand(N, seed=104)
+    ops.gemm(a, b, bias=bias, epi=ops.EPI_RESIDUAL, out=x, gate=gate, aux=y)
+    torch.testing.assert_close(y.float(), acc, rtol=1e-2, atol=1e-2)
+    torch.testing.assert_close(x, x0 + gate * y.float(), rtol=1e-4, atol=1e-4)
