@@ -287,7 +287,8 @@ extern "C" int prfl_gemm_bf16(const void* A, int64_t lda, int a_trans, const voi
                               int64_t ldc, const float* bias, const float* gate, void* aux_bf16, int64_t ldaux, int M,
                               int N, int K, int epi, int beta, prfl_stream_t stream) {
   PRFL_CHECK_ARCH();
-  PRFL_REQUIRE(M > 0 && N > 0 && K > 0 && K % 8 == 0 && N % 8 == 0, PRFL_E_SHAPE, "gemm: M=%d N=%d K=%d (need K%%8==0, N%%8==0)", M, N, K);
+  PRFL_REQUIRE(M > 0 && N > 0 && K > 0 && N % 8 == 0, PRFL_E_SHAPE, "gemm: M=%d N=%d K=%d (need N%%8==0)", M, N, K);
+  PRFL_REQUIRE(K % 8 == 0 || (a_trans && b_trans), PRFL_E_SHAPE, "gemm: K=%d must be a multiple of 8 unless both operands are transposed", K);
   PRFL_REQUIRE(epi >= PRFL_EPI_BF16 && epi <= PRFL_EPI_BF16_DGELU, PRFL_E_SHAPE, "gemm: unknown epilogue %d", epi);
   PRFL_REQUIRE(!(a_trans && M % 8 != 0), PRFL_E_SHAPE, "gemm: transposed A needs M%%8==0 (M=%d)", M);
   PRFL_REQUIRE(lda % 8 == 0 && ldb % 8 == 0 && ldc % 4 == 0 && lda >= (a_trans ? M : K) && ldb >= (b_trans ? N : K) && ldc >= N,

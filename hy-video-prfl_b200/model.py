@@ -77,6 +77,9 @@ class _Linear(nn.Linear):
         return w, b
 
     def forward(self, x):
+        if torch.is_grad_enabled() and (x.requires_grad or self.weight.requires_grad):
+            from .engine import LinearFn
+            return LinearFn.apply(x, self.weight, self.bias, self)
         w, b = self.operands()
         shp = x.shape
         x2 = x.reshape(-1, shp[-1])
@@ -287,29 +290,27 @@ class WanAttentionBlock(nn.Module):
         self.modulation = nn.Parameter(torch.randn(1, 6, dim) / dim ** 0.5)
 
     def forward(self, x, e, seq_lens, grid_sizes, freqs, context, context_lens, first_block_bf16_input=False):
-        """x: [B, L, C] fp32 residual stream (updated IN PLACE and returned), e: [B, 6, C] fp32,
-        context: [B, Lc, C] bf16.  `first_block_bf16_input` reproduces the reference's extra bf16
-        rounding of norm1's output in block 0, whose input is bf16 (model.py:345 with x.dtype == bf16)."""
-        assert e.dtype == torch.float32 and x.dtype == torch.float32 and x.is_contiguous()
-        B, L, C = x.shape
-        em = (self.modulation.detach().float() + e).contiguous()                   # [B, 6, C]
-        ctx = context if context.dtype == torch.bfloat16 else context.to(torch.bfloat16)
-        for i in range(B):
-            xi = x[i]
-            ei = em[i]
-            h = self.norm1(xi, shift=ei[0], scale=ei[1], round_bf16=first_block_bf16_input)
-            a = self.self_attn.attend(h.unsqueeze(0), seq_lens[i:i + 1], grid_sizes[i:i + 1])[0]
-            wo, bo = self.self_attn.o.operands()
-            ops.gemm(a, wo, bias=bo, epi=ops.EPI_RESIDUAL, out=xi, gate=ei[2])      # x += e2 * o(attn)
-            h = self.norm3(xi) if self.cross_attn_norm else ops.cast_bf16(xi)
-            a = self.cross_attn.attend(h.unsqueeze(0), ctx[i:i + 1], context_lens)[0]
-            wo, bo = self.cross_attn.o.operands()
-            ops.gemm(a, wo, bias=bo, epi=ops.EPI_RESIDUAL, out=xi)                  # x += o(cross)
-            h = self.norm2(xi, shift=ei[3], scale=ei[4])
-            w1, b1 = self.ffn[0].operands()
-            w2, b2 = self.ffn[2].operands()
-            f = ops.gemm(h, w1, bias=b1, epi=ops.EPI_BF16_GELU)
-            ops.gemm(f, w2, bias=b2, epi=ops.EPI_RESIDUAL, out=xi, gate=ei[5])      # x += e5 * ffn
+        """x: [B, L, C] fp32 residual stream, e: [B, 6, C] fp32, context: [B, Lc, C] bf16.
+        Without autograd the stream is updated IN PLACE and returned.  With autograd the block is one
+        autograd.Function that saves only its input and recomputes in backward (engine.BlockFn).
+        `first_block_bf16_input` reproduces the reference's extra bf16 rounding of norm1's output in block 0,
+        whose input is bf16 (model.py:345 with x.dtype == bf16)."""
+        assert e.dtype == torch.float32 and context_lens is None
+        from . import engine
+        grids = _grid_list(grid_sizes)
+        if x.dtype != torch.float32 or not x.is_contiguous():
+            x = x.float().contiguous()
+        if torch.is_grad_enabled() and (x.requires_grad or e.requires_grad or context.requires_grad
+                                        or any(p.requires_grad for p in self.parameters())):
+            names = tuple(engine.block_param_names(self))
+            return engine.BlockFn.apply(x, e, context, self, [int(v) for v in seq_lens], grids, first_block_bf16_input, names,
+                                        *self.parameters())
+        em = (self.modulation.detach().float() + e.detach()).contiguous()                    # [B, 6, C]
+        ctx = context.detach()
+        ctx = ctx if ctx.dtype == torch.bfloat16 else ctx.to(torch.bfloat16)
+        x = x.detach()
+        for i in range(x.shape[0]):
+            engine.block_forward(self, x[i], em[i], ctx[i].contiguous(), int(seq_lens[i]), grids[i], first_block_bf16_input)
         return x
 
 
@@ -329,7 +330,7 @@ class Head(nn.Module):
 
     def forward(self, x, e):
         assert e.dtype == torch.float32
-        m = (self.modulation.detach().float() + e.unsqueeze(1)).chunk(2, dim=1)
+        m = (self.modulation.float() + e.unsqueeze(1)).chunk(2, dim=1)
         h = F.layer_norm(x.float(), (self.dim,), None, None, self.eps) * (1 + m[1]) + m[0]
         return F.linear(h, self.head.weight.float(), self.head.bias.float())
 
@@ -355,6 +356,19 @@ class MLPProj(nn.Module):
         h = F.gelu(h.float()).to(torch.bfloat16)
         h = p[3](h)
         return F.layer_norm(h.float(), p[4].normalized_shape, p[4].weight.float(), p[4].bias.float(), p[4].eps)
+
+
+class _UnpatchifyFn(torch.autograd.Function):
+    """'fhwpqrc->cfphqwr' scatter (model.py:700-703) and its transpose."""
+
+    @staticmethod
+    def forward(ctx, tokens, c, grid):
+        ctx.rows = tokens.shape[0]
+        return ops.unpatchify(tokens.detach(), c, grid)
+
+    @staticmethod
+    def backward(ctx, dvid):
+        return ops.unpatchify_bwd(dvid.detach().float().contiguous(), ctx.rows), None, None
 
 
 class WanModel(nn.Module):
@@ -419,11 +433,16 @@ class WanModel(nn.Module):
         dev = self.patch_embedding.weight.device
         ctx = torch.stack([torch.cat([u, u.new_zeros(self.text_len - u.size(0), u.size(1))]) for u in context])
         ctx = ctx.to(device=dev, dtype=torch.bfloat16)
-        w0, b0 = self.text_embedding[0].operands()
-        w2, b2 = self.text_embedding[2].operands()
         B = ctx.shape[0]
-        h = ops.gemm(ctx.view(B * self.text_len, -1), w0, bias=b0, epi=ops.EPI_BF16_GELU)
-        ctx = ops.gemm(h, w2, bias=b2, epi=ops.EPI_BF16).view(B, self.text_len, self.dim)
+        if torch.is_grad_enabled() and any(p.requires_grad for p in self.text_embedding.parameters()):
+            h = self.text_embedding[0](ctx)                              # LinearFn (tcgen05 fwd, dgrad, wgrad)
+            h = F.gelu(h.float(), approximate="tanh").to(torch.bfloat16)
+            ctx = self.text_embedding[2](h)
+        else:
+            w0, b0 = self.text_embedding[0].operands()
+            w2, b2 = self.text_embedding[2].operands()
+            h = ops.gemm(ctx.view(B * self.text_len, -1), w0, bias=b0, epi=ops.EPI_BF16_GELU)
+            ctx = ops.gemm(h, w2, bias=b2, epi=ops.EPI_BF16).view(B, self.text_len, self.dim)
         if clip_fea is not None:
             ctx = torch.cat([self.img_emb(clip_fea.to(dev)).to(torch.bfloat16), ctx], dim=1)
         return ctx
@@ -438,18 +457,27 @@ class WanModel(nn.Module):
         assert not self.enable_teacache, "teacache is an inference-time heuristic outside this path"
         dev = self.patch_embedding.weight.device
         wp, bp = self._patch_operands()
+        train = torch.is_grad_enabled() and (any(p.requires_grad for p in self.parameters()) or any(u.requires_grad for u in x))
         embs, grids = [], []
         for i, u in enumerate(x):
-            yi = None if y is None else y[i].to(device=dev, dtype=torch.float32).contiguous()
-            patches = ops.patchify(u.to(device=dev, dtype=torch.float32).contiguous(), yi)
-            embs.append(ops.gemm(patches, wp, bias=bp, epi=ops.EPI_BF16))            # [L_i, dim] bf16, like the autocast conv
+            yi = None if y is None else y[i].to(device=dev)
+            if train:
+                from .engine import PatchEmbedFn
+                embs.append(PatchEmbedFn.apply(u.to(dev), yi, self.patch_embedding.weight, self.patch_embedding.bias, self))
+            else:
+                yf = None if yi is None else yi.to(torch.float32).contiguous()
+                patches = ops.patchify(u.to(device=dev, dtype=torch.float32).contiguous(), yf)
+                embs.append(ops.gemm(patches, wp, bias=bp, epi=ops.EPI_BF16))        # [L_i, dim] bf16, like the autocast conv
             grids.append((u.shape[1] // self.patch_size[0], u.shape[2] // self.patch_size[1], u.shape[3] // self.patch_size[2]))
         seq_lens = torch.tensor([e_.size(0) for e_ in embs], dtype=torch.long)
         grid_sizes = torch.tensor(grids, dtype=torch.long)
         assert int(seq_lens.max()) <= seq_len
-        xs = torch.zeros(len(embs), seq_len, self.dim, dtype=torch.float32, device=dev)
-        for i, e_ in enumerate(embs):
-            xs[i, :e_.size(0)] = e_
+        if train:
+            xs = torch.stack([torch.cat([e_.float(), e_.new_zeros(seq_len - e_.size(0), self.dim, dtype=torch.float32)]) for e_ in embs])
+        else:
+            xs = torch.zeros(len(embs), seq_len, self.dim, dtype=torch.float32, device=dev)
+            for i, e_ in enumerate(embs):
+                xs[i, :e_.size(0)] = e_
 
         # time embeddings — fp32 (model.py:589-594); tiny, PyTorch
         tt = t.to(dev)
@@ -469,7 +497,10 @@ class WanModel(nn.Module):
             xs = block(xs, e=e0, seq_lens=seq_lens, grid_sizes=grid_sizes, freqs=self.freqs, context=ctx,
                        context_lens=None, first_block_bf16_input=(index == 0))
             if output_features and index + 1 in selected_layers:
-                features_list.append(all_gather(xs, dim=1) if get_sequence_parallel_state() else xs.clone())
+                if get_sequence_parallel_state():
+                    features_list.append(all_gather(xs, dim=1))
+                else:
+                    features_list.append(xs if xs.requires_grad else xs.clone())
         if output_features:
             return features_list
 
@@ -480,7 +511,7 @@ class WanModel(nn.Module):
 
     def unpatchify(self, x, grid_sizes, c):
         """model.py:683-705."""
-        return [ops.unpatchify(u[:math.prod(g)].float().contiguous(), c, g) for u, g in zip(x, _grid_list(grid_sizes))]
+        return [_UnpatchifyFn.apply(u[:math.prod(g)].float().contiguous(), c, g) for u, g in zip(x, _grid_list(grid_sizes))]
 
     def init_weights(self):
         """model.py:707-729."""

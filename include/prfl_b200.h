@@ -103,7 +103,8 @@ int prfl_gate_bwd(const float* dx, const void* y_bf16, const float* gate, void* 
  *   PRFL_EPI_BF16_DGELU out_bf16[m,n]  = bf16(acc * gelu_tanh'(aux_bf16[m,n]))   (FFN backward; aux is an INPUT)
  * With PRFL_EPI_BF16_GELU or PRFL_EPI_RESIDUAL a non-NULL aux_bf16 [M, N] (ldaux) is an extra OUTPUT that receives
  * bf16(acc + bias[n]) — the pre-activation / the un-gated branch output the backward needs.
- * bias: [N] f32 or NULL.  M,N,K > 0; K % 8 == 0; N % 8 == 0; lda/ldb/ldc % 8 == 0. */
+ * bias: [N] f32 or NULL.  M,N,K > 0; N % 8 == 0; K % 8 == 0 unless both operands are transposed (wgrad over a ragged token count);
+ * lda/ldb/ldc % 8 == 0. */
 #define PRFL_EPI_BF16 0
 #define PRFL_EPI_BF16_GELU 1
 #define PRFL_EPI_F32 2
