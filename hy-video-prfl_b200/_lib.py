@@ -29,6 +29,7 @@ _SIGS = {
     "prfl_launch_count": (_i64, []),
     "prfl_launch_count_reset": (None, []),
     "prfl_ln_mod_fwd": (C.c_int, [_p, _p, _p, _p, _p, _p, _p, _p, _i64, _i32, _f32, _i32, _p]),
+    "prfl_ln_mod_split_fwd": (C.c_int, [_p, _p, _p, _p, _p, _i64, _i32, _f32, _p]),
     "prfl_rmsnorm_rope_fwd": (C.c_int, [_p, _i64, _p, _p, _p, _p, _i64, _p, _i64, _i32, _i64, _i64, _f32, _p]),
     "prfl_gemm_bf16": (C.c_int, [_p, _i64, _i32, _p, _i64, _i32, _p, _i64, _p, _p, _p, _i64, _i32, _i32, _i32, _i32, _i32, _p]),
     "prfl_attn_fwd": (C.c_int, [_p, _i64, _i64, _p, _i64, _i64, _p, _i64, _i64, _p, _i64, _i64, _p, _i32, _i32, _i32, _f32, _p]),

@@ -18,7 +18,8 @@ __global__ void __launch_bounds__(128) ln_mod_fwd_kernel(const float* __restrict
                                                          const float* __restrict__ scale, const float* __restrict__ gamma,
                                                          const float* __restrict__ beta, __nv_bfloat16* __restrict__ out,
                                                          float* __restrict__ mean_out, float* __restrict__ rstd_out,
-                                                         int64_t rows, float eps, int round_bf16) {
+                                                         int64_t rows, float eps, int round_bf16,
+                                                         __nv_bfloat16* __restrict__ out_lo = nullptr) {
   constexpr int C = NCH * 256;
   const int lane = threadIdx.x & 31;
   const int64_t warp_global = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -80,6 +81,14 @@ __global__ void __launch_bounds__(128) ln_mod_fwd_kernel(const float* __restrict
       o.x = pack_bf16x2(y[0], y[1]); o.y = pack_bf16x2(y[2], y[3]);
       o.z = pack_bf16x2(y[4], y[5]); o.w = pack_bf16x2(y[6], y[7]);
       stg_v4(orow + c0, o);
+      if (out_lo) {  // residual of the bf16 rounding: y = hi + lo to ~16 mantissa bits (fp32-grade head GEMM)
+        float r[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) r[j] = y[j] - bf16_round(y[j]);
+        o.x = pack_bf16x2(r[0], r[1]); o.y = pack_bf16x2(r[2], r[3]);
+        o.z = pack_bf16x2(r[4], r[5]); o.w = pack_bf16x2(r[6], r[7]);
+        stg_v4(out_lo + row * C + c0, o);
+      }
     }
   }
 }
@@ -307,6 +316,25 @@ int prfl_ln_mod_fwd(const float* x, const float* shift, const float* scale, cons
         x, shift, scale, gamma, beta, (__nv_bfloat16*)out_bf16, mean, rstd, rows, eps, round_bf16);
     count_launch();
     PRFL_LAUNCH_CHECK("ln_mod_fwd");
+    return PRFL_OK;
+  });
+}
+
+int prfl_ln_mod_split_fwd(const float* x, const float* shift, const float* scale, void* out_hi_bf16, void* out_lo_bf16,
+                          int64_t rows, int C, float eps, prfl_stream_t stream) {
+  PRFL_CHECK_ARCH();
+  PRFL_REQUIRE(rows >= 0 && C > 0 && C % 256 == 0 && out_hi_bf16 && out_lo_bf16, PRFL_E_SHAPE, "ln_mod_split_fwd: rows=%lld C=%d",
+               (long long)rows, C);
+  PRFL_REQUIRE((shift == nullptr) == (scale == nullptr), PRFL_E_SHAPE, "ln_mod_split_fwd: shift/scale come in pairs");
+  PRFL_REQUIRE(aligned16(x) && aligned16(out_hi_bf16) && aligned16(out_lo_bf16) && aligned16(shift) && aligned16(scale), PRFL_E_ALIGN,
+               "ln_mod_split_fwd: pointers must be 16-byte aligned");
+  if (rows == 0) return PRFL_OK;
+  return dispatch_nch(C, [&](auto nch) {
+    constexpr int NCH = decltype(nch)::value;
+    ln_mod_fwd_kernel<NCH><<<row_grid(rows, 4, 8), 128, 0, (cudaStream_t)stream>>>(
+        x, shift, scale, nullptr, nullptr, (__nv_bfloat16*)out_hi_bf16, nullptr, nullptr, rows, eps, 0, (__nv_bfloat16*)out_lo_bf16);
+    count_launch();
+    PRFL_LAUNCH_CHECK("ln_mod_split_fwd");
     return PRFL_OK;
   });
 }

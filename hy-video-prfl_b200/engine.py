@@ -161,7 +161,7 @@ def _wgrad(dy: torch.Tensor, x: torch.Tensor) -> torch.Tensor:
     return ops.gemm(dy, x, a_trans=True, b_trans=True, epi=ops.EPI_F32)
 
 
-def block_backward(blk, st: Dict, dx: torch.Tensor, need_ctx_grad: bool):
+def block_backward(blk, st: Dict, dx: torch.Tensor, need_ctx_grad: bool, need_w: bool = True):
     """dx: [M, C] fp32 gradient w.r.t. the block output; overwritten with the gradient w.r.t. the block input.
     Returns (grads: name -> fp32 tensor, dem [6, C], dctx [Lc, C] fp32 or None)."""
     sa, ca = blk.self_attn, blk.cross_attn
@@ -169,6 +169,9 @@ def block_backward(blk, st: Dict, dx: torch.Tensor, need_ctx_grad: bool):
     n, d = sa.num_heads, sa.head_dim
     em = st["em"]
     g: Dict[str, torch.Tensor] = {}
+    # frozen blocks (PRFL's reward model, Appendix B item 10): dgrad only, every weight-gradient kernel is skipped
+    wgrad = _wgrad if need_w else (lambda dy, x: None)
+    colsum = ops.colsum if need_w else (lambda a: None)
 
     # ---- FFN ----
     w1, b1 = blk.ffn[0].operands()
@@ -177,12 +180,12 @@ def block_backward(blk, st: Dict, dx: torch.Tensor, need_ctx_grad: bool):
     dy2, de5 = ops.gate_bwd(dx, y2, em[5])
     del y2
     du = ops.gemm(dy2, w2, b_trans=True, epi=ops.EPI_BF16_DGELU, aux=st["u"])                # [M, ffn]
-    g["ffn.2.weight"] = _wgrad(dy2, st["f"])
-    g["ffn.2.bias"] = ops.colsum(dy2)
+    g["ffn.2.weight"] = wgrad(dy2, st["f"])
+    g["ffn.2.bias"] = colsum(dy2)
     del dy2
     dh2 = ops.gemm(du, w1, b_trans=True, epi=ops.EPI_BF16)                                   # [M, C]
-    g["ffn.0.weight"] = _wgrad(du, st["h2"])
-    g["ffn.0.bias"] = ops.colsum(du)
+    g["ffn.0.weight"] = wgrad(du, st["h2"])
+    g["ffn.0.bias"] = colsum(du)
     del du
     dsh2, dsc2 = ops.ln_mod_bwd(st["x2"], dh2, em[4], None, st["mean2"], st["rstd2"], dx, True)
     del dh2
@@ -191,8 +194,8 @@ def block_backward(blk, st: Dict, dx: torch.Tensor, need_ctx_grad: bool):
     dyc, _ = ops.gate_bwd(dx, None, None)                                                     # bf16 cast of dx
     wco, _ = ca.o.operands()
     da2 = ops.gemm(dyc, wco, b_trans=True, epi=ops.EPI_BF16)
-    g["cross_attn.o.weight"] = _wgrad(dyc, st["a2"])
-    g["cross_attn.o.bias"] = ops.colsum(dyc)
+    g["cross_attn.o.weight"] = wgrad(dyc, st["a2"])
+    g["cross_attn.o.bias"] = colsum(dyc)
     del dyc
     q2_3 = st["q2"].unflatten(1, (n, d))
     da2_3 = da2.unflatten(1, (n, d))
@@ -208,23 +211,24 @@ def block_backward(blk, st: Dict, dx: torch.Tensor, need_ctx_grad: bool):
         dq2 = dq_g if dq2 is None else dq2 + dq_g
         kn, vn = cg["names"]
         nname = "cross_attn.norm_k_img.weight" if kn == "k_img" else "cross_attn.norm_k.weight"
-        g[nname] = ops.rmsnorm_rope_bwd_(cg["k_raw"], _f(cg["norm"].weight), None, None, dkv[:, :C], cg["rstd"])
+        g[nname] = ops.rmsnorm_rope_bwd_(cg["k_raw"], _f(cg["norm"].weight), None, None, dkv[:, :C], cg["rstd"], need_dw=need_w)
         wkv, _ = ca._kv_operands(cg["names"])
-        dwkv = _wgrad(dkv, cg["c_in"])                                                        # [2C, C]
-        g[f"cross_attn.{kn}.weight"], g[f"cross_attn.{vn}.weight"] = dwkv[:C], dwkv[C:]
-        dbkv = ops.colsum(dkv)
-        g[f"cross_attn.{kn}.bias"], g[f"cross_attn.{vn}.bias"] = dbkv[:C], dbkv[C:]
+        if need_w:
+            dwkv = wgrad(dkv, cg["c_in"])                                                    # [2C, C]
+            g[f"cross_attn.{kn}.weight"], g[f"cross_attn.{vn}.weight"] = dwkv[:C], dwkv[C:]
+            dbkv = colsum(dkv)
+            g[f"cross_attn.{kn}.bias"], g[f"cross_attn.{vn}.bias"] = dbkv[:C], dbkv[C:]
         if need_ctx_grad:
             dctx_parts.append(ops.gemm(dkv, wkv, b_trans=True, epi=ops.EPI_F32))              # [Lc, C]
     dq2 = dq2.reshape(M, C)
-    g["cross_attn.norm_q.weight"] = ops.rmsnorm_rope_bwd_(st["q2_raw"], _f(ca.norm_q.weight), None, None, dq2, st["rstd_q2"])
+    g["cross_attn.norm_q.weight"] = ops.rmsnorm_rope_bwd_(st["q2_raw"], _f(ca.norm_q.weight), None, None, dq2, st["rstd_q2"], need_dw=need_w)
     wcq, _ = ca.q.operands()
     dh3 = ops.gemm(dq2, wcq, b_trans=True, epi=ops.EPI_BF16)
-    g["cross_attn.q.weight"] = _wgrad(dq2, st["h3"])
-    g["cross_attn.q.bias"] = ops.colsum(dq2)
+    g["cross_attn.q.weight"] = wgrad(dq2, st["h3"])
+    g["cross_attn.q.bias"] = colsum(dq2)
     del dq2, da2
     if blk.cross_attn_norm:
-        db3, dg3 = ops.ln_mod_bwd(st["x1"], dh3, None, _f(blk.norm3.weight), st["mean3"], st["rstd3"], dx, True)
+        db3, dg3 = ops.ln_mod_bwd(st["x1"], dh3, None, _f(blk.norm3.weight), st["mean3"], st["rstd3"], dx, need_w)
         g["norm3.weight"], g["norm3.bias"] = dg3, db3
     else:
         dx += dh3.float()
@@ -234,8 +238,8 @@ def block_backward(blk, st: Dict, dx: torch.Tensor, need_ctx_grad: bool):
     dy1, de2 = ops.gate_bwd(dx, st["y1"], em[2])
     wo, _ = sa.o.operands()
     da1 = ops.gemm(dy1, wo, b_trans=True, epi=ops.EPI_BF16)
-    g["self_attn.o.weight"] = _wgrad(dy1, st["a1"])
-    g["self_attn.o.bias"] = ops.colsum(dy1)
+    g["self_attn.o.weight"] = wgrad(dy1, st["a1"])
+    g["self_attn.o.bias"] = colsum(dy1)
     del dy1
     qkv = st["qkv"]
     klen, P = st["klen"], st["P"]
@@ -257,16 +261,17 @@ def block_backward(blk, st: Dict, dx: torch.Tensor, need_ctx_grad: bool):
     del da1
     qk_raw = st["qk_raw"]
     g["self_attn.norm_q.weight"] = ops.rmsnorm_rope_bwd_(qk_raw[:, :C], _f(sa.norm_q.weight), st["cos"], st["sin"], dqkv[:, :C],
-                                                        st["rstd_q"], st["n_rot"], st["pos0"])
+                                                        st["rstd_q"], st["n_rot"], st["pos0"], need_dw=need_w)
     g["self_attn.norm_k.weight"] = ops.rmsnorm_rope_bwd_(qk_raw[:, C:], _f(sa.norm_k.weight), st["cos"], st["sin"], dqkv[:, C:2 * C],
-                                                        st["rstd_k"], st["n_rot"], st["pos0"])
+                                                        st["rstd_k"], st["n_rot"], st["pos0"], need_dw=need_w)
     wqkv, _ = sa._qkv_operands()
     dh1 = ops.gemm(dqkv, wqkv, b_trans=True, epi=ops.EPI_BF16)                               # [M, C]
-    dwqkv = _wgrad(dqkv, st["h1"])                                                            # [3C, C]
-    dbqkv = ops.colsum(dqkv)
-    for j, nm in enumerate(("q", "k", "v")):
-        g[f"self_attn.{nm}.weight"] = dwqkv[j * C:(j + 1) * C]
-        g[f"self_attn.{nm}.bias"] = dbqkv[j * C:(j + 1) * C]
+    if need_w:
+        dwqkv = wgrad(dqkv, st["h1"])                                                        # [3C, C]
+        dbqkv = colsum(dqkv)
+        for j, nm in enumerate(("q", "k", "v")):
+            g[f"self_attn.{nm}.weight"] = dwqkv[j * C:(j + 1) * C]
+            g[f"self_attn.{nm}.bias"] = dbqkv[j * C:(j + 1) * C]
     del dqkv
     dsh1, dsc1 = ops.ln_mod_bwd(st["x_in"], dh1, em[1], None, st["mean1"], st["rstd1"], dx, True)
     dem = torch.stack([dsh1, dsc1, de2, dsh2, dsc2, de5])                                     # [6, C]
@@ -308,19 +313,22 @@ class BlockFn(torch.autograd.Function):
         cb = context.detach()
         cb = cb if cb.dtype == torch.bfloat16 else cb.to(torch.bfloat16)
         need_ctx = ctx.needs_input_grad[2]
+        need_w = any(ctx.needs_input_grad[8:])
         tot: Dict[str, torch.Tensor] = {}
         dems, dctxs = [], []
         for i in range(B):
             st: Dict = {}
             block_forward(blk, x[i].detach().clone(), em[i], cb[i].contiguous(), int(ctx.seq_lens[i]), ctx.grids[i], ctx.first, st)
-            gi, dem, dctx = block_backward(blk, st, dx[i], need_ctx)
+            gi, dem, dctx = block_backward(blk, st, dx[i], need_ctx, need_w)
             del st
             for k, v in gi.items():
-                tot[k] = v if k not in tot else tot[k] + v
+                if v is not None:
+                    tot[k] = v if k not in tot else tot[k] + v
             dems.append(dem)
             dctxs.append(dctx)
         de = torch.stack(dems)                                                                # [B, 6, C]
-        tot["modulation"] = de.sum(0, keepdim=True)
+        if need_w:
+            tot["modulation"] = de.sum(0, keepdim=True)
         dctx = torch.stack(dctxs).to(context.dtype) if need_ctx else None
         pg = []
         for nm, p in zip(ctx.names, ctx.blk.parameters()):

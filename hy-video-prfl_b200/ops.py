@@ -80,6 +80,19 @@ def ln_mod(x: torch.Tensor, shift=None, scale=None, gamma=None, beta=None, eps: 
     return (out, mean, rstd) if save_stats else out
 
 
+def ln_mod_split(x: torch.Tensor, shift, scale, eps: float = 1e-6):
+    """LayerNorm + modulate with the result split into a bf16 (hi, lo) pair: hi + lo == fp32 result to ~16 bits."""
+    _req(x, f32, "ln_mod_split.x")
+    assert x.is_contiguous()
+    C = x.shape[-1]
+    rows = x.numel() // C
+    hi = torch.empty(x.shape, dtype=bf16, device=x.device)
+    lo = torch.empty(x.shape, dtype=bf16, device=x.device)
+    check(lib().prfl_ln_mod_split_fwd(_p(x), _p(shift), _p(scale), _p(hi), _p(lo), rows, C, float(eps), _stream()),
+          "prfl_ln_mod_split_fwd")
+    return hi, lo
+
+
 def rmsnorm_rope_(x: torch.Tensor, w: torch.Tensor, cos: Optional[torch.Tensor], sin: Optional[torch.Tensor],
                   eps: float, n_rot: int = 0, pos0: int = 0, out: Optional[torch.Tensor] = None,
                   save_rstd: bool = False):

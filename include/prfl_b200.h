@@ -63,6 +63,13 @@ int prfl_ln_mod_fwd(const float* x, const float* shift, const float* scale, cons
 int prfl_rmsnorm_rope_fwd(const void* x_bf16, int64_t ldx, const float* w, const float* cos_tab, const float* sin_tab,
                           void* out_bf16, int64_t ldo, float* rstd, int64_t rows, int C, int64_t n_rot, int64_t pos0,
                           float eps, prfl_stream_t stream);
+/* Head (model.py:379-389) runs its LayerNorm + modulate + Linear(dim -> 64) in fp32 in the reference.  Here the
+ * modulated row h is emitted as a bf16 pair h = hi + lo (lo = bf16(h - hi), ~16 mantissa bits) and the Linear is three
+ * tensor-core GEMMs hi.Whi + hi.Wlo + lo.Whi accumulated in fp32 (prfl_gemm_bf16, PRFL_EPI_F32 with beta): fp32-grade
+ * result (relative error ~1e-5) from the bf16 tensor pipe.  out_hi/out_lo: [rows, C] bf16. */
+int prfl_ln_mod_split_fwd(const float* x, const float* shift, const float* scale, void* out_hi_bf16, void* out_lo_bf16,
+                          int64_t rows, int C, float eps, prfl_stream_t stream);
+
 /* ---- backward of the two norm kernels + the token-dimension reductions ---------------------------
  * Replace what autograd derives for model.py:345,352,353 (LayerNorm + modulate / affine), model.py:106-122 + 60-103
  * (RMSNorm + RoPE) and the bias / modulation / gate / norm-weight gradient reductions over tokens.

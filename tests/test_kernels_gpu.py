@@ -320,3 +320,23 @@ def test_gemm_aux_outputs(ops):
     ops.gemm(a, b, bias=bias, epi=ops.EPI_RESIDUAL, out=x, gate=gate, aux=y)
     torch.testing.assert_close(y.float(), acc, rtol=1e-2, atol=1e-2)
     torch.testing.assert_close(x, x0 + gate * y.float(), rtol=1e-4, atol=1e-4)
+
+
+def test_head_split_gemm_is_fp32_grade(ops):
+    """LayerNorm+modulate emitted as a bf16 (hi, lo) pair + three tensor-core GEMMs == fp32 Linear to ~1e-5."""
+    M, C, N = 777, 1536, 64
+    x = _rand(M, C, seed=110) * 2
+    sh, sc = _rand(C, seed=111), _rand(C, seed=112) * 0.3
+    w = _rand(N, C, seed=113) * 0.05
+    bias = _rand(N, seed=114)
+    hi, lo = ops.ln_mod_split(x, sh, sc)
+    ref_h = torch.nn.functional.layer_norm(x, (C,), None, None, 1e-6) * (1 + sc) + sh
+    assert float((hi.float() + lo.float() - ref_h).abs().max()) < 2e-4
+    w_hi = w.bfloat16()
+    w_lo = (w - w_hi.float()).bfloat16()
+    o = ops.gemm(hi, w_hi, bias=bias, epi=ops.EPI_F32)
+    ops.gemm(hi, w_lo, epi=ops.EPI_F32, out=o, beta=True)
+    ops.gemm(lo, w_hi, epi=ops.EPI_F32, out=o, beta=True)
+    ref = (ref_h.double() @ w.double().t() + bias.double()).float()
+    cos, rel = cos_rel(o, ref)
+    assert cos > 0.9999999 and rel < 5e-5, (cos, rel)

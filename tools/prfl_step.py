@@ -1,0 +1,124 @@
+"""A PRFL `train_step_refl`-shaped step (scripts/prfl/train_prfl.py:585-898 of the reference) on the B200 path, at a
+depth that fits one GPU with fp32 master weights + fp32 gradients:
+
+  1. `m` no-grad DiT forwards of the trainable video model (VGM, `--blocks` Wan-14B blocks)      [train_prfl.py:665-699]
+  2. one forward WITH grad (per-block recompute in backward)                                      [:723-725]
+  3. a differentiable scheduler step latent' = latent - dt * noise_pred (stand-in for UniPC.step, out of scope) [:734]
+  4. frozen reward model: 8-block Wan-14B features -> QueryAttention -> MLP -> loss 0.1*relu(2 - r) [:764-798]
+  5. backward through 4 -> 3 -> 2 (dgrad only through the reward model; its weight grads are never used, Appendix B.10)
+
+Prints one JSON object with per-phase milliseconds and algorithmic TFLOP/s (SURVEY.md Appendix A per-block numbers).
+Not the bench.py headline (that is BASELINE configs[1]); numbers go to profiles/.
+"""
+import argparse
+import json
+import os
+import sys
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--blocks", type=int, default=8)
+    ap.add_argument("--m", type=int, default=2)
+    ap.add_argument("--latent", default="21,60,104")
+    ap.add_argument("--steps", type=int, default=2)
+    args = ap.parse_args()
+    import torch.distributed as dist
+    from prfl_b200 import _lib, parallel
+    from prfl_b200.model import WanModel
+    from prfl_b200.network import MLP, QueryAttention
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+        parallel.initialize_sequence_parallel_state(world)
+    fr, hh, ww = (int(v) for v in args.latent.split(","))
+    L = fr * (hh // 2) * (ww // 2)
+    torch.manual_seed(0)
+    with torch.device(dev):
+        vgm = WanModel(model_type="t2v", dim=5120, ffn_dim=13824, num_heads=40, num_layers=args.blocks)
+        vgm.head.head.weight.data.normal_(0, 0.02)                  # the reference zero-inits it (model.py:729)
+        lrm = WanModel(model_type="t2v", dim=5120, ffn_dim=13824, num_heads=40, num_layers=8)
+        lrm.head = None
+        qa = QueryAttention(5120, 1, 8, dropout=0.0, return_type="query")
+        mlp = MLP(5120)
+    for mod in (lrm, qa, mlp):
+        for p in mod.parameters():
+            p.requires_grad_(False)                                 # frozen reward model: dgrad only
+    vgm.train()
+    latent = torch.randn(16, fr, hh, ww, device=dev)
+    ctx = [torch.randn(512, 4096, device=dev) * 0.08]
+    dt = 0.025
+
+    def ev():
+        e = torch.cuda.Event(enable_timing=True)
+        e.record()
+        return e
+
+    def one_step():
+        marks = {"start": ev()}
+        lat = latent
+        with torch.no_grad():
+            for i in range(args.m):
+                t = torch.tensor([999.0 - 25 * i], device=dev)
+                pred = vgm(x=[lat], t=t, context=ctx, seq_len=L)[0]
+                lat = lat - dt * pred
+        marks["nograd_done"] = ev()
+        t = torch.tensor([999.0 - 25 * args.m], device=dev)
+        pred = vgm(x=[lat], t=t, context=ctx, seq_len=L)[0]
+        marks["grad_fwd_done"] = ev()
+        lat2 = lat - dt * pred
+        feats = torch.stack(lrm(x=[lat2], t=t - 25, context=ctx, seq_len=L, output_features=True, selected_layers=[8]))
+        reward = mlp(qa(feats))
+        loss = 0.1 * torch.relu(2.0 - reward).mean()
+        marks["lrm_fwd_done"] = ev()
+        loss.backward()
+        marks["bwd_done"] = ev()
+        return marks, float(loss)
+
+    one_step()                                                      # warm-up (operand caches, allocator)
+    vgm.zero_grad(set_to_none=True)
+    torch.cuda.synchronize()
+    rows = []
+    _lib.launch_count_reset()
+    for _ in range(args.steps):
+        marks, loss = one_step()
+        torch.cuda.synchronize()
+        k = list(marks)
+        rows.append({k[i + 1]: marks[k[i]].elapsed_time(marks[k[i + 1]]) for i in range(len(k) - 1)})
+        vgm.zero_grad(set_to_none=True)
+    avg = {k: sum(r[k] for r in rows) / len(rows) for k in rows[0]}
+    # algorithmic FLOPs per block at this L (SURVEY.md Appendix A formulae)
+    lin = 597.7e6 * L + 4 * 5120 * 5120 * 512
+    att = 4.0 * L * L * 128 * 40 + 4.0 * L * 512 * 128 * 40
+    fwd_blk = (lin + att) / world
+    bwd_blk = (2 * lin + 2.5 * att) / world
+    nb = args.blocks
+    out = {
+        "workload": f"PRFL refl-shaped step, VGM {nb} blocks (14B dims) + frozen 8-block reward model, L={L}, m={args.m}, SP={world}",
+        "ms": avg, "loss": loss, "gpu_launches_per_step": _lib.launch_count() / args.steps,
+        "nograd_fwd_tflops": args.m * nb * fwd_blk / (avg["nograd_done"] * 1e-3) / 1e12 if args.m else None,
+        "grad_fwd_tflops": nb * fwd_blk / (avg["grad_fwd_done"] * 1e-3) / 1e12,
+        "lrm_fwd_tflops": 8 * fwd_blk / (avg["lrm_fwd_done"] * 1e-3) / 1e12,
+        # backward = recompute fwd + bwd of the VGM blocks, and recompute + dgrad (here: full bwd kernels) of 8 LRM blocks
+        "bwd_tflops_algorithmic": ((nb + 8) * (fwd_blk + bwd_blk)) / (avg["bwd_done"] * 1e-3) / 1e12,
+        "step_ms": sum(avg.values()),
+        "peak_mem_gb": torch.cuda.max_memory_allocated() / 1e9,
+    }
+    if int(os.environ.get("RANK", "0")) == 0:
+        print(json.dumps(out, indent=1))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
