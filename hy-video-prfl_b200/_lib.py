@@ -39,6 +39,9 @@ _SIGS = {
     "prfl_colsum_bf16": (C.c_int, [_p, _i64, _p, _i64, _i32, _p]),
     "prfl_gate_bwd": (C.c_int, [_p, _p, _p, _p, _p, _i64, _i32, _p]),
     "prfl_attn_bwd": (C.c_int, [_p, _i64, _i64] * 5 + [_p, _p] + [_p, _i64, _i64] * 3 + [_i32, _i32, _i32, _f32, _p]),
+    "prfl_attn_fwd_p2p": (C.c_int, [_p, _i64, _i64, _p, _i64, _i64, _p, _i64, _i64, _p, _i32, _i32, _i32, _i64, _i64, _p, _i32, _i32,
+                                    _i32, _f32, _p]),
+    "prfl_a2a_scatter_p2p": (C.c_int, [_p, _i64, _i64, _p, _i32, _i32, _i32, _i32, _p]),
     "prfl_patchify": (C.c_int, [_p, _i32, _p, _i32, _p, _i32, _i32, _i32, _p]),
     "prfl_patchify_bwd": (C.c_int, [_p, _i32, _i32, _p, _i32, _i32, _i32, _p]),
     "prfl_unpatchify": (C.c_int, [_p, _p, _i32, _i32, _i32, _i32, _i32, _p]),

@@ -29,6 +29,10 @@ struct AttnFwdParams {
   float* lse;
   int Lq, Lk;
   float scale_log2;
+  // Ulysses output exchange fused into the epilogue: row i belongs to rank i / L_loc and is stored straight into that
+  // rank's [L_loc, H_total, 128] buffer over NVLink (peer-mapped pointers), at head head_off + h.  n_peer == 0: off.
+  __nv_bfloat16* o_peer[8];
+  int n_peer, L_loc, head_off;
 };
 
 __global__ void __launch_bounds__(ATT_THREADS, 1)
@@ -235,7 +239,13 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     tc_fence_after();
     const float inv_l = 1.0f / l_sum;
     const bool row_ok = row < p.Lq;
-    __nv_bfloat16* orow = p.o + (int64_t)row * p.o_ld_tok + (int64_t)head * p.o_ld_head;
+    __nv_bfloat16* orow;
+    if (p.n_peer > 0) {
+      const int r = row_ok ? row / p.L_loc : 0;
+      orow = p.o_peer[r] + (int64_t)(row - r * p.L_loc) * p.o_ld_tok + (int64_t)(p.head_off + head) * p.o_ld_head;
+    } else {
+      orow = p.o + (int64_t)row * p.o_ld_tok + (int64_t)head * p.o_ld_head;
+    }
 #pragma unroll 1
     for (int c = 0; c < 4; ++c) {
       uint32_t o[32];
@@ -269,14 +279,17 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
 
 using namespace prfl;
 
-extern "C" int prfl_attn_fwd(const void* q, int64_t q_ld_tok, int64_t q_ld_head, const void* k, int64_t k_ld_tok,
-                             int64_t k_ld_head, const void* v, int64_t v_ld_tok, int64_t v_ld_head, void* o, int64_t o_ld_tok,
-                             int64_t o_ld_head, float* lse, int Lq, int Lk, int H, float scale, prfl_stream_t stream) {
+static int attn_fwd_launch(const void* q, int64_t q_ld_tok, int64_t q_ld_head, const void* k, int64_t k_ld_tok, int64_t k_ld_head,
+                           const void* v, int64_t v_ld_tok, int64_t v_ld_head, void* o, int64_t o_ld_tok, int64_t o_ld_head,
+                           float* lse, int Lq, int Lk, int H, float scale, void* const* o_peers, int n_peer, int L_loc,
+                           int head_off, prfl_stream_t stream) {
   PRFL_CHECK_ARCH();
   PRFL_REQUIRE(Lq > 0 && Lk > 0 && H > 0, PRFL_E_SHAPE, "attn_fwd: Lq=%d Lk=%d H=%d", Lq, Lk, H);
   PRFL_REQUIRE(q_ld_tok % 8 == 0 && q_ld_head % 8 == 0 && k_ld_tok % 8 == 0 && k_ld_head % 8 == 0 && v_ld_tok % 8 == 0 &&
                    v_ld_head % 8 == 0 && o_ld_tok % 8 == 0 && o_ld_head % 8 == 0 && (reinterpret_cast<uintptr_t>(o) & 15) == 0,
                PRFL_E_ALIGN, "attn_fwd: strides must be multiples of 8 elements, pointers 16-byte aligned");
+  PRFL_REQUIRE(n_peer >= 0 && n_peer <= 8 && (n_peer == 0 || (o_peers && L_loc > 0 && (int64_t)L_loc * n_peer >= Lq)), PRFL_E_SHAPE,
+               "attn_fwd: n_peer=%d L_loc=%d Lq=%d", n_peer, L_loc, Lq);
   CUtensorMap tmQ, tmK, tmV;
   int rc = make_tmap_3d(&tmQ, q, HD, (uint64_t)Lq, (uint64_t)H, (uint64_t)q_ld_tok * 2, (uint64_t)q_ld_head * 2, 64, QT, 1, 1);
   if (rc != PRFL_OK) return rc;
@@ -293,9 +306,27 @@ extern "C" int prfl_attn_fwd(const void* q, int64_t q_ld_tok, int64_t q_ld_head,
   AttnFwdParams p;
   p.o = (__nv_bfloat16*)o; p.o_ld_tok = o_ld_tok; p.o_ld_head = o_ld_head; p.lse = lse; p.Lq = Lq; p.Lk = Lk;
   p.scale_log2 = scale * 1.4426950408889634f;
+  p.n_peer = n_peer; p.L_loc = L_loc; p.head_off = head_off;
+  for (int i = 0; i < 8; ++i) p.o_peer[i] = i < n_peer ? (__nv_bfloat16*)o_peers[i] : nullptr;
   dim3 grid((Lq + 2 * QT - 1) / (2 * QT), H);
   attn_fwd_kernel<<<grid, ATT_THREADS, ATT_SMEM, (cudaStream_t)stream>>>(tmQ, tmK, tmV, p);
   count_launch();
   PRFL_LAUNCH_CHECK("attn_fwd");
   return PRFL_OK;
+}
+
+extern "C" int prfl_attn_fwd(const void* q, int64_t q_ld_tok, int64_t q_ld_head, const void* k, int64_t k_ld_tok,
+                             int64_t k_ld_head, const void* v, int64_t v_ld_tok, int64_t v_ld_head, void* o, int64_t o_ld_tok,
+                             int64_t o_ld_head, float* lse, int Lq, int Lk, int H, float scale, prfl_stream_t stream) {
+  return attn_fwd_launch(q, q_ld_tok, q_ld_head, k, k_ld_tok, k_ld_head, v, v_ld_tok, v_ld_head, o, o_ld_tok, o_ld_head, lse, Lq, Lk,
+                         H, scale, nullptr, 0, 0, 0, stream);
+}
+
+extern "C" int prfl_attn_fwd_p2p(const void* q, int64_t q_ld_tok, int64_t q_ld_head, const void* k, int64_t k_ld_tok,
+                                 int64_t k_ld_head, const void* v, int64_t v_ld_tok, int64_t v_ld_head, void* const* o_peers,
+                                 int n_peer, int L_loc, int head_off, int64_t o_ld_tok, int64_t o_ld_head, float* lse, int Lq,
+                                 int Lk, int H, float scale, prfl_stream_t stream) {
+  PRFL_REQUIRE(n_peer >= 1 && o_peers, PRFL_E_SHAPE, "attn_fwd_p2p: needs peer pointers");
+  return attn_fwd_launch(q, q_ld_tok, q_ld_head, k, k_ld_tok, k_ld_head, v, v_ld_tok, v_ld_head, o_peers[0], o_ld_tok, o_ld_head, lse,
+                         Lq, Lk, H, scale, o_peers, n_peer, L_loc, head_off, stream);
 }

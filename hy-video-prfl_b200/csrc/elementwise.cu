@@ -268,6 +268,27 @@ __global__ void a2a_pack_kernel(__nv_bfloat16* __restrict__ strided, int64_t ld_
   }
 }
 
+// Ulysses q/k/v exchange without NCCL: every rank stores its token chunk straight into the peers' receive buffers
+// (peer-mapped NVLink pointers): peer[p][(rank*L_loc + t), hl, :] = strided[t][p*Hl + hl][:]
+struct PeerPtrs {
+  __nv_bfloat16* p[8];
+};
+__global__ void a2a_scatter_p2p_kernel(const __nv_bfloat16* __restrict__ strided, int64_t ld_tok, int64_t ld_head, PeerPtrs peers,
+                                       int L_loc, int H, int P, int rank) {
+  const int Hl = H / P;
+  const int64_t total = (int64_t)P * L_loc * Hl * 16;
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+    int piece = (int)(idx & 15);
+    int64_t t = idx >> 4;
+    int hl = (int)(t % Hl);
+    t /= Hl;
+    int tok = (int)(t % L_loc);
+    int p = (int)(t / L_loc);
+    const uint4 v = *reinterpret_cast<const uint4*>(strided + (int64_t)tok * ld_tok + (int64_t)(p * Hl + hl) * ld_head + piece * 8);
+    *reinterpret_cast<uint4*>(peers.p[p] + (((int64_t)rank * L_loc + tok) * Hl + hl) * 128 + piece * 8) = v;
+  }
+}
+
 template <typename F>
 static int dispatch_nch(int C, F&& f) {
   switch (C / 256) {
@@ -427,6 +448,23 @@ int prfl_a2a_pack(void* strided, int64_t ld_tok, int64_t ld_head, void* packed, 
                                                                                         (__nv_bfloat16*)packed, L_loc, H, P, mode);
   count_launch();
   PRFL_LAUNCH_CHECK("a2a_pack");
+  return PRFL_OK;
+}
+
+int prfl_a2a_scatter_p2p(const void* strided, int64_t ld_tok, int64_t ld_head, void* const* peer_recv, int L_loc, int H, int P,
+                         int rank, prfl_stream_t stream) {
+  PRFL_CHECK_ARCH();
+  PRFL_REQUIRE(L_loc > 0 && H > 0 && P > 0 && P <= 8 && H % P == 0 && rank >= 0 && rank < P && peer_recv, PRFL_E_SHAPE,
+               "a2a_scatter_p2p: L_loc=%d H=%d P=%d rank=%d", L_loc, H, P, rank);
+  PRFL_REQUIRE(aligned16(strided) && ld_tok % 8 == 0 && ld_head % 8 == 0, PRFL_E_ALIGN, "a2a_scatter_p2p: alignment");
+  PeerPtrs pp;
+  for (int i = 0; i < 8; ++i) pp.p[i] = i < P ? (__nv_bfloat16*)peer_recv[i] : nullptr;
+  int64_t total = (int64_t)L_loc * H * 16;
+  int64_t blocks = (total + 255) / 256, cap = (int64_t)sm_count() * 16;
+  a2a_scatter_p2p_kernel<<<(int)(blocks < cap ? blocks : cap), 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)strided, ld_tok,
+                                                                                               ld_head, pp, L_loc, H, P, rank);
+  count_launch();
+  PRFL_LAUNCH_CHECK("a2a_scatter_p2p");
   return PRFL_OK;
 }
 

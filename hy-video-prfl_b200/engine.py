@@ -18,7 +18,8 @@ from typing import Dict, List, Optional, Tuple
 import torch
 
 from . import ops
-from .parallel import get_sequence_parallel_state, nccl_info, ulysses_gather_tokens, ulysses_scatter_tokens
+from .parallel import (get_p2p_ulysses, get_sequence_parallel_state, nccl_info, ulysses_gather_tokens,
+                       ulysses_scatter_tokens)
 from .rope import rope_tables
 
 T5_CONTEXT_TOKEN_NUMBER = 512
@@ -71,12 +72,18 @@ def block_forward(blk, x: torch.Tensor, em: torch.Tensor, ctx: torch.Tensor, seq
             a1 = ops.attn_fwd(q3, k3[:klen], v3[:klen])
         qg = kg = vg = og = None
     else:
-        qg, kg, vg = (ulysses_scatter_tokens(t, P) for t in (q3, k3, v3))                    # [L, n/P, d]
-        if keep:
-            og, lse1 = ops.attn_fwd(qg, kg[:klen], vg[:klen], need_lse=True)
+        p2p = None if keep else get_p2p_ulysses(M * P, n, x.device)
+        if p2p is not None:
+            # no-grad forward: both exchanges are peer stores fused into our own kernels (no NCCL, no staging copies)
+            a1 = p2p.attention(q3, k3, v3, klen)                                             # [M, n, d] (symmetric buffer)
+            qg = kg = vg = og = None
         else:
-            og = ops.attn_fwd(qg, kg[:klen], vg[:klen])
-        a1 = ulysses_gather_tokens(og, P)                                                    # [M, n, d]
+            qg, kg, vg = (ulysses_scatter_tokens(t, P) for t in (q3, k3, v3))                # [L, n/P, d]
+            if keep:
+                og, lse1 = ops.attn_fwd(qg, kg[:klen], vg[:klen], need_lse=True)
+            else:
+                og = ops.attn_fwd(qg, kg[:klen], vg[:klen])
+            a1 = ulysses_gather_tokens(og, P)                                                # [M, n, d]
     a1 = a1.reshape(M, C)
     wo, bo = sa.o.operands()
     y1 = torch.empty(M, C, dtype=torch.bfloat16, device=x.device) if keep else None

@@ -253,6 +253,35 @@ def gate_bwd(dx: torch.Tensor, y: Optional[torch.Tensor], gate: Optional[torch.T
     return dy, (part.sum(0) if part is not None else None)
 
 
+def _ptr_array(ptrs):
+    import ctypes
+    return (ctypes.c_void_p * len(ptrs))(*[int(p) for p in ptrs])
+
+
+def a2a_scatter_p2p(strided: torch.Tensor, peer_recv_ptrs, P: int, rank: int):
+    """q/k/v exchange as direct NVLink stores: peer[p][(rank*L_loc + t), hl, :] = strided[t, p*H/P + hl, :]."""
+    _req(strided, bf16, "a2a_scatter_p2p.src")
+    L_loc, H, d = strided.shape
+    assert d == 128 and strided.stride(2) == 1 and len(peer_recv_ptrs) == P
+    check(lib().prfl_a2a_scatter_p2p(_p(strided), strided.stride(0), strided.stride(1), _ptr_array(peer_recv_ptrs), L_loc, H, P,
+                                     rank, _stream()), "prfl_a2a_scatter_p2p")
+
+
+def attn_fwd_p2p(q, k, v, o_peer_ptrs, L_loc: int, head_off: int, H_total: int, scale: Optional[float] = None):
+    """attn_fwd whose epilogue stores row i into rank (i // L_loc)'s [L_loc, H_total, 128] buffer (peer pointers)."""
+    for t, n in ((q, "q"), (k, "k"), (v, "v")):
+        _req(t, bf16, "attn_p2p." + n)
+        assert t.dim() == 3 and t.shape[2] == 128 and t.stride(2) == 1
+    Lq, H, _ = q.shape
+    Lk = k.shape[0]
+    if scale is None:
+        scale = 1.0 / math.sqrt(128)
+    with _timed("attn_fwd_self" if Lk > 1024 else "attn_fwd_cross"):
+        check(lib().prfl_attn_fwd_p2p(_p(q), q.stride(0), q.stride(1), _p(k), k.stride(0), k.stride(1), _p(v), v.stride(0), v.stride(1),
+                                      _ptr_array(o_peer_ptrs), len(o_peer_ptrs), L_loc, head_off, H_total * 128, 128, None, Lq, Lk, H,
+                                      float(scale), _stream()), "prfl_attn_fwd_p2p")
+
+
 def cast_bf16(src: torch.Tensor) -> torch.Tensor:
     _req(src, f32, "cast.src")
     assert src.is_contiguous()

@@ -179,3 +179,59 @@ class _AllGather(torch.autograd.Function):
 def all_gather(input_: torch.Tensor, dim: int = 1):
     """communication.py:263-273."""
     return _AllGather.apply(input_, dim)
+
+
+# ------------------------------------------------------------------------------------------------
+# NCCL-free Ulysses exchange for the no-grad forward: peer stores over NVLink into symmetric buffers
+# ------------------------------------------------------------------------------------------------
+class P2PUlysses:
+    """Symmetric (peer-mapped) receive buffers + the two fused exchanges of one self-attention:
+         q/k/v : prfl_a2a_scatter_p2p — every rank stores its token chunk's heads straight into the owners' buffers
+         out   : prfl_attn_fwd_p2p    — the attention epilogue stores each query row straight into its home rank
+    with one cross-rank barrier after each (torch symmetric-memory signal pads).  Replaces 4 NCCL all-to-alls, the pack
+    and the unpack copies per block (communication.py:40-160 does 4 all_to_all_single + 8 transposes + 4 device syncs)."""
+
+    def __init__(self, L: int, H: int, device):
+        import torch.distributed._symmetric_memory as symm_mem
+        self.P, self.rank = nccl_info.sp_size, nccl_info.rank_within_group
+        self.L, self.H = L, H
+        self.L_loc, self.Hl = L // self.P, H // self.P
+        self.qkv = symm_mem.empty(3, L, self.Hl, 128, dtype=torch.bfloat16, device=device)
+        self.o = symm_mem.empty(self.L_loc, H, 128, dtype=torch.bfloat16, device=device)
+        self.h_qkv = symm_mem.rendezvous(self.qkv, nccl_info.group)
+        self.h_o = symm_mem.rendezvous(self.o, nccl_info.group)
+        self.qkv_ptrs = [int(p) for p in self.h_qkv.buffer_ptrs]
+        self.o_ptrs = [int(p) for p in self.h_o.buffer_ptrs]
+        self.slab = L * self.Hl * 128 * 2
+
+    def attention(self, q3: torch.Tensor, k3: torch.Tensor, v3: torch.Tensor, klen: int) -> torch.Tensor:
+        """q3/k3/v3: local [L/P, H, 128] bf16 views.  Returns this rank's [L/P, H, 128] attention output (a view of the
+        symmetric buffer: consume it before the next call)."""
+        from . import ops
+        for j, t in enumerate((q3, k3, v3)):
+            ops.a2a_scatter_p2p(t, [p + j * self.slab for p in self.qkv_ptrs], self.P, self.rank)
+        self.h_qkv.barrier(channel=0)
+        ops.attn_fwd_p2p(self.qkv[0], self.qkv[1][:klen], self.qkv[2][:klen], self.o_ptrs, self.L_loc, self.rank * self.Hl, self.H)
+        self.h_o.barrier(channel=1)
+        return self.o
+
+
+_p2p_cache = {}
+_p2p_disabled = os.environ.get("PRFL_ULYSSES", "p2p").lower() == "nccl"
+
+
+def get_p2p_ulysses(L: int, H: int, device) -> Optional[P2PUlysses]:
+    """The peer-store exchange if symmetric memory can be set up on this box, else None (=> NCCL all-to-all path)."""
+    global _p2p_disabled
+    if _p2p_disabled or not get_sequence_parallel_state() or nccl_info.sp_size > 8:
+        return None
+    key = (L, H, str(device))
+    if key not in _p2p_cache:
+        try:
+            _p2p_cache[key] = P2PUlysses(L, H, device)
+        except Exception as e:  # no fabric / no peer access: keep NCCL
+            import warnings
+            warnings.warn(f"prfl_b200: symmetric-memory Ulysses unavailable ({type(e).__name__}: {e}); using NCCL all-to-all")
+            _p2p_disabled = True
+            return None
+    return _p2p_cache[key]

@@ -1,0 +1,127 @@
+"""Sharded gradients + optimizer state for the trainable Wan-DiT (the FSDP FULL_SHARD role in the reference,
+diffusers_lite/utils/fsdp_utils.py:66-122 + train_prfl.py:346-362, 482-491), re-cut for 180 GB B200s.
+
+The reference shards parameters, gradients and AdamW state over ALL ranks (SP ranks included) and all-gathers every
+block's fp32 parameters twice per step (1.41 GB per block per direction).  With 180 GB per GPU the 14B bf16 operands
+(28 GB) fit replicated, so this build keeps the *compute copies* resident and shards only what is large and cold:
+
+  * per FSDP unit (one per WanAttentionBlock + one root unit, `_no_split_modules`), gradients are flattened and
+    REDUCE-SCATTERED (fp32, averaged over the world group exactly as FSDP does — under Ulysses every rank holds the
+    partial gradient of its token chunk) so each rank keeps 1/W of them;
+  * fp32 master weights and AdamW moments exist only as 1/W shards;
+  * after the update the new parameters are ALL-GATHERED once per step (not per block per pass).
+
+Collectives are NCCL through torch.distributed (`reduce_scatter_tensor` / `all_gather_into_tensor`); on backends
+without reduce-scatter (gloo, used by the CPU tests) the same result is produced with all_reduce + slice.
+"""
+from __future__ import annotations
+
+import math
+from typing import Iterable, List, Optional
+
+import torch
+import torch.distributed as dist
+import torch.nn as nn
+
+
+def fsdp_units(model: nn.Module) -> List[List[nn.Parameter]]:
+    """One unit per block (load.py:6-12 wraps WanAttentionBlock) + a root unit with everything else."""
+    units, seen = [], set()
+    blocks = getattr(model, "blocks", [])
+    for blk in blocks:
+        ps = [p for p in blk.parameters() if p.requires_grad]
+        seen.update(id(p) for p in ps)
+        if ps:
+            units.append(ps)
+    root = [p for p in model.parameters() if p.requires_grad and id(p) not in seen]
+    if root:
+        units.append(root)
+    return units
+
+
+class ShardedAdamW:
+    """AdamW over reduce-scattered gradient shards with sharded fp32 masters and moments (ZeRO-2 layout)."""
+
+    def __init__(self, model: nn.Module, lr=1e-5, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0, group=None,
+                 average: bool = True):
+        self.group = group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.lr, self.betas, self.eps, self.wd, self.average = lr, betas, eps, weight_decay, average
+        self.units = fsdp_units(model)
+        self.state = []
+        for ps in self.units:
+            n = sum(p.numel() for p in ps)
+            pad = (-n) % self.world
+            shard = (n + pad) // self.world
+            flat = torch.cat([p.detach().reshape(-1).float() for p in ps])
+            if pad:
+                flat = torch.cat([flat, flat.new_zeros(pad)])
+            master = flat[self.rank * shard:(self.rank + 1) * shard].clone()
+            self.state.append(dict(n=n, pad=pad, shard=shard, master=master, m=torch.zeros_like(master),
+                                   v=torch.zeros_like(master), t=0))
+
+    # -- collectives --------------------------------------------------------------------------------
+    def _reduce_scatter(self, flat: torch.Tensor, shard: int) -> torch.Tensor:
+        if self.world == 1:
+            return flat
+        op = dist.ReduceOp.AVG if (self.average and dist.get_backend(self.group) == "nccl") else dist.ReduceOp.SUM
+        if dist.get_backend(self.group) == "nccl":
+            out = torch.empty(shard, dtype=flat.dtype, device=flat.device)
+            dist.reduce_scatter_tensor(out, flat, op=op, group=self.group)
+            return out
+        dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.group)       # gloo path (tests): same numbers
+        out = flat[self.rank * shard:(self.rank + 1) * shard].clone()
+        return out / self.world if self.average else out
+
+    def _all_gather(self, shard_t: torch.Tensor) -> torch.Tensor:
+        if self.world == 1:
+            return shard_t
+        out = torch.empty(self.world * shard_t.numel(), dtype=shard_t.dtype, device=shard_t.device)
+        dist.all_gather_into_tensor(out, shard_t, group=self.group)
+        return out
+
+    # -- API ------------------------------------------------------------------------------------------
+    def reduce_gradients(self) -> List[torch.Tensor]:
+        """Flatten + reduce-scatter every unit's gradients; frees the full-size .grad tensors. Returns the shards."""
+        shards = []
+        for ps, st in zip(self.units, self.state):
+            flat = torch.cat([(p.grad if p.grad is not None else torch.zeros_like(p)).reshape(-1).float() for p in ps])
+            if st["pad"]:
+                flat = torch.cat([flat, flat.new_zeros(st["pad"])])
+            for p in ps:
+                p.grad = None
+            shards.append(self._reduce_scatter(flat, st["shard"]))
+        return shards
+
+    def clip_grad_norm_(self, shards: List[torch.Tensor], max_norm: float) -> torch.Tensor:
+        """Global L2 norm over all shards of all ranks (FSDP.clip_grad_norm_, train_prfl.py:825)."""
+        sq = torch.stack([s.pow(2).sum() for s in shards]).sum()
+        if self.world > 1:
+            dist.all_reduce(sq, group=self.group)
+        norm = sq.sqrt()
+        coef = torch.clamp(max_norm / (norm + 1e-6), max=1.0)
+        for s in shards:
+            s.mul_(coef)
+        return norm
+
+    @torch.no_grad()
+    def step(self, shards: Optional[List[torch.Tensor]] = None, max_norm: Optional[float] = None):
+        shards = self.reduce_gradients() if shards is None else shards
+        norm = self.clip_grad_norm_(shards, max_norm) if max_norm is not None else None
+        b1, b2 = self.betas
+        for ps, st, g in zip(self.units, self.state, shards):
+            st["t"] += 1
+            t = st["t"]
+            w, m, v = st["master"], st["m"], st["v"]
+            w.mul_(1 - self.lr * self.wd)
+            m.mul_(b1).add_(g, alpha=1 - b1)
+            v.mul_(b2).addcmul_(g, g, value=1 - b2)
+            denom = (v.sqrt() / math.sqrt(1 - b2 ** t)).add_(self.eps)
+            w.addcdiv_(m, denom, value=-self.lr / (1 - b1 ** t))
+            full = self._all_gather(w)
+            off = 0
+            for p in ps:
+                p.data.copy_(full[off:off + p.numel()].view_as(p))      # bumps p._version => bf16 operand caches refresh
+                off += p.numel()
+        return norm

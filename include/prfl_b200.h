@@ -132,6 +132,14 @@ int prfl_gemm_bf16(const void* A, int64_t lda, int a_trans, const void* B, int64
 int prfl_attn_fwd(const void* q, int64_t q_ld_tok, int64_t q_ld_head, const void* k, int64_t k_ld_tok,
                   int64_t k_ld_head, const void* v, int64_t v_ld_tok, int64_t v_ld_head, void* o, int64_t o_ld_tok,
                   int64_t o_ld_head, float* lse, int Lq, int Lk, int H, float scale, prfl_stream_t stream);
+/* Same kernel with the Ulysses output exchange (model.py:195-196, communication.py:91-123) fused into its epilogue:
+ * this rank computed H = H_total/P heads over all Lq tokens; row i is stored directly into rank (i / L_loc)'s
+ * [L_loc, H_total, 128] buffer o_peers[i / L_loc] (peer-mapped NVLink pointer; HOST array of n_peer device pointers) at
+ * token i % L_loc, head head_off + h.  No NCCL call, no staging copy.  The caller barriers across ranks before reading. */
+int prfl_attn_fwd_p2p(const void* q, int64_t q_ld_tok, int64_t q_ld_head, const void* k, int64_t k_ld_tok,
+                      int64_t k_ld_head, const void* v, int64_t v_ld_tok, int64_t v_ld_head, void* const* o_peers,
+                      int n_peer, int L_loc, int head_off, int64_t o_ld_tok, int64_t o_ld_head, float* lse, int Lq, int Lk,
+                      int H, float scale, prfl_stream_t stream);
 /* Backward (replaces flash_attn's bwd kernels reached through autograd from the same call sites): dq, dk, dv (bf16,
  * same addressing as q/k/v) from q, k, v, o, dout and the forward's lse.  delta: [H, Lq] f32 workspace, filled here
  * with rowsum(dout * o).  Two tcgen05 kernels (dK/dV with keys resident, dQ with queries resident); no atomics. */
@@ -184,6 +192,11 @@ int prfl_cast_f32_bf16(const float* src, void* dst_bf16, int64_t n, prfl_stream_
  * already is the send buffer.  strided: element (t, h, d) at t*ld_tok + h*ld_head + d, t < L_loc, h < H. */
 int prfl_a2a_pack(void* strided, int64_t ld_tok, int64_t ld_head, void* packed, int L_loc, int H, int P, int mode,
                   prfl_stream_t stream);
+
+/* The q/k/v exchange (model.py:183-186) as direct peer stores: peer_recv[p][(rank*L_loc + t), hl, :] = strided[t][p*(H/P)+hl][:]
+ * where peer_recv is a HOST array of P peer-mapped device pointers to each rank's [P*L_loc, H/P, 128] receive buffer. */
+int prfl_a2a_scatter_p2p(const void* strided, int64_t ld_tok, int64_t ld_head, void* const* peer_recv, int L_loc, int H, int P,
+                         int rank, prfl_stream_t stream);
 
 #ifdef __cplusplus
 }
