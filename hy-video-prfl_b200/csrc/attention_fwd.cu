@@ -167,68 +167,101 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     const uint32_t o_addr = tmem_base + 256 + t * 128 + lane_off;
     float m_used = -INFINITY;  // max the exponentials are currently relative to (log2 domain)
     float l_sum = 0.f;
+    const float2 sc2 = make_float2(p.scale_log2, p.scale_log2);
     for (int j = 0; j < n_kv; ++j) {
       mbar_wait(&sfull[t], j & 1);
       tc_fence_after();
-      uint32_t r[4][32];
+      const int valid = p.Lk - j * KT;  // columns >= valid are padding (TMA zero fill); only the last tile is ragged
+      uint32_t pk[64];                  // P as packed bf16x2, stored over S only after the max check below
+      float tile_sum = 0.f, tile_max = -INFINITY;
+      // One pass over S (two 64-column halves straight from TMEM): P = exp2(S*c - m_ref), row sum, raw row max.
+      auto exp_pass = [&](const float m_ref) {
+        const float2 neg_m2 = make_float2(-m_ref, -m_ref);
+        float2 acc0 = make_float2(0.f, 0.f), acc1 = make_float2(0.f, 0.f);
+        float mx0 = -INFINITY, mx1 = -INFINITY;
 #pragma unroll
-      for (int c = 0; c < 4; ++c) tmem_ld32(s_addr + c * 32, r[c]);
-      tmem_wait_ld();
-      const int valid = p.Lk - j * KT;  // columns >= valid are padding (TMA zero fill)
-      if (valid < KT) {                 // tail tile only (warp-uniform)
+        for (int c = 0; c < 4; c += 2) {
+          uint32_t r0[32], r1[32];
+          tmem_ld32(s_addr + c * 32, r0);
+          tmem_ld32(s_addr + (c + 1) * 32, r1);
+          tmem_wait_ld();
+          if (valid < KT) {
 #pragma unroll
-        for (int c = 0; c < 4; ++c)
+            for (int i = 0; i < 32; ++i) {
+              if (c * 32 + i >= valid) r0[i] = 0xff800000u;  // -inf
+              if ((c + 1) * 32 + i >= valid) r1[i] = 0xff800000u;
+            }
+          }
 #pragma unroll
-          for (int i = 0; i < 32; ++i)
-            if (c * 32 + i >= valid) r[c][i] = 0xff800000u;  // -inf
-      }
-      float mx0 = -INFINITY, mx1 = -INFINITY;
-#pragma unroll
-      for (int c = 0; c < 4; ++c)
-#pragma unroll
-        for (int i = 0; i < 32; i += 4) {
-          mx0 = fmax3(mx0, __uint_as_float(r[c][i]), __uint_as_float(r[c][i + 1]));
-          mx1 = fmax3(mx1, __uint_as_float(r[c][i + 2]), __uint_as_float(r[c][i + 3]));
+          for (int i = 0; i < 32; i += 2) {
+            mx0 = fmax3(mx0, __uint_as_float(r0[i]), __uint_as_float(r0[i + 1]));
+            mx1 = fmax3(mx1, __uint_as_float(r1[i]), __uint_as_float(r1[i + 1]));
+            float2 xa = ffma2(make_float2(__uint_as_float(r0[i]), __uint_as_float(r0[i + 1])), sc2, neg_m2);
+            float2 xb = ffma2(make_float2(__uint_as_float(r1[i]), __uint_as_float(r1[i + 1])), sc2, neg_m2);
+            float2 pa, pb;
+            if (((i >> 1) & 3) == 3) {   // 1 pair in 4 goes to the FMA pipe instead of MUFU (compile-time pattern)
+              pa = exp2_fma2(xa);
+              pb = exp2_fma2(xb);
+            } else {
+              pa = make_float2(fast_exp2(xa.x), fast_exp2(xa.y));
+              pb = make_float2(fast_exp2(xb.x), fast_exp2(xb.y));
+            }
+            acc0 = fadd2(acc0, pa);
+            acc1 = fadd2(acc1, pb);
+            pk[c * 16 + (i >> 1)] = pack_bf16x2(pa.x, pa.y);        // keys 32c + i, +1       -> packed column 16c + i/2
+            pk[c * 16 + 16 + (i >> 1)] = pack_bf16x2(pb.x, pb.y);   // keys 32(c+1) + i, +1   -> packed column 16(c+1) + i/2
+          }
         }
-      const float mx = fmaxf(mx0, mx1);
-      const float m_new = fmaxf(m_used, mx * p.scale_log2);
+        tile_sum = (acc0.x + acc0.y) + (acc1.x + acc1.y);
+        tile_max = fmaxf(mx0, mx1);
+      };
       if (j == 0) {
-        m_used = m_new;
-      } else if (__any_sync(0xffffffffu, m_new > m_used + 8.0f)) {
-        // rescale O (warp-uniform branch: tcgen05.ld/st are warp-collective)
-        const float alpha = fast_exp2(m_used - m_new);
-        l_sum *= alpha;
-        m_used = m_new;
-#pragma unroll 1
-        for (int c = 0; c < 4; ++c) {
-          uint32_t o[32];
-          tmem_ld32(o_addr + c * 32, o);
+        // first tile: the reference max must be the true row max (one extra read of S from TMEM)
+        float mx0 = -INFINITY, mx1 = -INFINITY;
+#pragma unroll
+        for (int c = 0; c < 4; c += 2) {
+          uint32_t r0[32], r1[32];
+          tmem_ld32(s_addr + c * 32, r0);
+          tmem_ld32(s_addr + (c + 1) * 32, r1);
           tmem_wait_ld();
 #pragma unroll
-          for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
-          tmem_st32(o_addr + c * 32, o);
+          for (int i = 0; i < 32; i += 2) {
+            if (c * 32 + i + 1 < valid) mx0 = fmax3(mx0, __uint_as_float(r0[i]), __uint_as_float(r0[i + 1]));
+            else if (c * 32 + i < valid) mx0 = fmaxf(mx0, __uint_as_float(r0[i]));
+            if ((c + 1) * 32 + i + 1 < valid) mx1 = fmax3(mx1, __uint_as_float(r1[i]), __uint_as_float(r1[i + 1]));
+            else if ((c + 1) * 32 + i < valid) mx1 = fmaxf(mx1, __uint_as_float(r1[i]));
+          }
+        }
+        m_used = fmaxf(mx0, mx1) * p.scale_log2;
+        exp_pass(m_used);
+      } else {
+        // optimistic: exponentiate against the stale max while tracking this tile's max; exact unless the max grew
+        // by more than 8 (log2 units), in which case O and l are rescaled and the tile is redone (rare after tile 0)
+        exp_pass(m_used);
+        const float m_new = fmaxf(m_used, tile_max * p.scale_log2);
+        if (__any_sync(0xffffffffu, m_new > m_used + 8.0f)) {   // warp-uniform: tcgen05.ld/st are warp-collective
+          const float alpha = fast_exp2(m_used - m_new);
+          l_sum *= alpha;
+          m_used = m_new;
+#pragma unroll 1
+          for (int c = 0; c < 4; ++c) {
+            uint32_t o[32];
+            tmem_ld32(o_addr + c * 32, o);
+            tmem_wait_ld();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+            tmem_st32(o_addr + c * 32, o);
+          }
+          exp_pass(m_used);
         }
       }
-      const float2 neg_m2 = make_float2(-m_used, -m_used);
-      const float2 sc2 = make_float2(p.scale_log2, p.scale_log2);
-      float2 acc0 = make_float2(0.f, 0.f), acc1 = make_float2(0.f, 0.f);
-#pragma unroll
-      for (int c = 0; c < 4; c += 2) {
-        uint32_t pk[32];
-#pragma unroll
-        for (int i = 0; i < 32; i += 2) {
-          float2 xa = ffma2(make_float2(__uint_as_float(r[c][i]), __uint_as_float(r[c][i + 1])), sc2, neg_m2);
-          float2 xb = ffma2(make_float2(__uint_as_float(r[c + 1][i]), __uint_as_float(r[c + 1][i + 1])), sc2, neg_m2);
-          float2 pa = make_float2(fast_exp2(xa.x), fast_exp2(xa.y));
-          float2 pb = make_float2(fast_exp2(xb.x), fast_exp2(xb.y));
-          acc0 = fadd2(acc0, pa);
-          acc1 = fadd2(acc1, pb);
-          pk[i >> 1] = pack_bf16x2(pa.x, pa.y);
-          pk[16 + (i >> 1)] = pack_bf16x2(pb.x, pb.y);
-        }
-        tmem_st32(s_addr + c * 16, pk);  // P columns [32*(c/2), +32) hold keys [64*(c/2), +64)
+      l_sum += tile_sum;
+      {
+        uint32_t(&lo)[32] = *reinterpret_cast<uint32_t(*)[32]>(&pk[0]);
+        uint32_t(&hi)[32] = *reinterpret_cast<uint32_t(*)[32]>(&pk[32]);
+        tmem_st32(s_addr, lo);        // packed columns [0,32)  = keys [0,64)
+        tmem_st32(s_addr + 32, hi);   // packed columns [32,64) = keys [64,128)
       }
-      l_sum += (acc0.x + acc0.y) + (acc1.x + acc1.y);
       tmem_wait_st();
       tc_fence_before();
       __syncwarp();

@@ -139,10 +139,18 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       int m_blk, n_blk;
       tile_coords(tile, p.tiles_m, p.tiles_n, m_blk, n_blk);
       const uint32_t buf = t & 1, aph = (t >> 1) & 1;
-      mbar_wait(&tfull[buf], aph);
-      tc_fence_after();
       const int row = m_blk * BM + quad * 32 + lane;
       const bool row_ok = row < p.M;
+      if ((p.epi == PRFL_EPI_RESIDUAL || (p.epi == PRFL_EPI_F32 && p.beta)) && row_ok) {
+        // the read-modify-write epilogue is latency-bound on the fp32 tile it updates: pull this thread's row segment
+        // (1 KB = 8 lines) into L2 now, while the tile's main loop is still running
+        const float* o = reinterpret_cast<const float*>(p.out) + (int64_t)row * p.ldc + n_blk * BN;
+#pragma unroll
+        for (int j = 0; j < BN / 32; ++j)
+          if (n_blk * BN + j * 32 < p.N) asm volatile("prefetch.global.L2 [%0];" ::"l"(o + j * 32));
+      }
+      mbar_wait(&tfull[buf], aph);
+      tc_fence_after();
       const uint32_t taddr = tmem_base + buf * BN + ((uint32_t)(quad * 32) << 16);
       const int n0 = n_blk * BN;
 #pragma unroll 1

@@ -25,7 +25,7 @@ def main():
     parallel.initialize_sequence_parallel_state(world)
     ok = True
     # heads must divide by P and tokens by P: a 4-head model on a latent with 4*k tokens
-    cfg = synth.tiny_cfg("t2v", heads=4, layers=2, ffn=768)
+    cfg = synth.tiny_cfg("t2v", heads=max(4, world), layers=2, ffn=768)
     sd = synth.make_wan_state_dict(cfg, 50)
     inp = synth.make_inputs(cfg, (4, 12, 16), 51)           # grid 4 x 6 x 8 = 192 tokens
     assert inp["seq_len"] % world == 0
