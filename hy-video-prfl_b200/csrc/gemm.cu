@@ -10,12 +10,21 @@
 
 namespace prfl {
 
-constexpr int BM = 128, BN = 256, BK = 64, STAGES = 4;
+constexpr int BM = 128, BN = 256, BK = 64;
 constexpr int A_STAGE = BM * BK * 2;  // 16 KB
-constexpr int B_STAGE = BN * BK * 2;  // 32 KB
 constexpr int GEMM_THREADS = 192;
-constexpr int GEMM_SMEM = STAGES * (A_STAGE + B_STAGE) + 256 + 1024;  // + barriers + alignment slack
 constexpr int GROUP_M = 8;
+// CG = 1: one CTA per 128 x 256 tile, B stage 32 KB, 4 stages.
+// CG = 2: a CTA pair (cluster of 2, tcgen05 cta_group::2) per 256 x 256 tile: each CTA stages its 128 rows of A and HALF
+//         of B (128 of the 256 columns), the leader issues UMMA 256x256x16 that reads both CTAs' shared memory and writes
+//         both CTAs' TMEM.  Per-SM operand traffic from L2 and shared memory drops from 48 KB to 32 KB per k-block
+//         (96 -> 64 B/clk), which is what a power-capped B200 needs to hold its clocks; 6 stages fit.
+template <int CG> struct GemmCfg {
+  static constexpr int STAGES = CG == 2 ? 6 : 4;
+  static constexpr int B_ROWS = BN / CG;
+  static constexpr int B_STAGE = B_ROWS * BK * 2;
+  static constexpr int SMEM = STAGES * (A_STAGE + B_STAGE) + 256 + 1024;  // + barriers + alignment slack
+};
 
 struct GemmParams {
   void* out;
@@ -38,9 +47,13 @@ __device__ __forceinline__ void tile_coords(int tile, int tiles_m, int tiles_n, 
   n_blk = r / gm;
 }
 
-template <bool A_T, bool B_T>
+template <bool A_T, bool B_T, int CG>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
+  constexpr int STAGES = GemmCfg<CG>::STAGES, B_STAGE = GemmCfg<CG>::B_STAGE, B_ROWS = GemmCfg<CG>::B_ROWS;
+  const uint32_t cta_rank = CG == 2 ? cluster_ctarank() : 0;   // position inside the CTA pair
+  const bool leader = cta_rank == 0;
+  const int unit = blockIdx.x / CG, n_units = gridDim.x / CG;  // a "unit" = the CTA (pair) that owns whole tiles
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);  // SWIZZLE_128B tiles need 1024-B alignment
   uint8_t* sA = smem;
@@ -59,56 +72,66 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
     for (int s = 0; s < STAGES; ++s) {
-      mbar_init(&full[s], 1);
+      mbar_init(&full[s], CG);     // CG == 2: one arrive (+ the TMA bytes) from each CTA's producer, on the leader's barrier
       mbar_init(&empty[s], 1);
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(&tfull[b], 1);
-      mbar_init(&tempty[b], 4);
+      mbar_init(&tempty[b], 4 * CG);  // CG == 2: the epilogue warps of BOTH CTAs release the leader's barrier
     }
     fence_barrier_init();
   }
-  if (warp == 1) tmem_alloc<512>(tmem_slot);
+  if (warp == 1) {
+    if (CG == 2) tmem_alloc_cg2<512>(tmem_slot);
+    else tmem_alloc<512>(tmem_slot);
+  }
   tc_fence_before();
-  __syncthreads();
+  if (CG == 2) cluster_sync_all();   // peer barriers are initialised before anyone arrives on them remotely
+  else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
     if (lane == 0) {
       uint32_t it = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      auto load = [&](void* dst, const CUtensorMap* tm, uint64_t* bar, int c0, int c1) {
+        if (CG == 2) tma_load_2d_cg2(dst, tm, bar, c0, c1);   // bytes are credited to the leader CTA's barrier
+        else tma_load_2d(dst, tm, bar, c0, c1);
+      };
+      for (int tile = unit; tile < total_tiles; tile += n_units) {
         int m_blk, n_blk;
         tile_coords(tile, p.tiles_m, p.tiles_n, m_blk, n_blk);
-        const int m0 = m_blk * BM, n0 = n_blk * BN;
+        const int m0 = (m_blk * CG + cta_rank) * BM, n0 = n_blk * BN + cta_rank * B_ROWS;
         for (int kb = 0; kb < p.num_kb; ++kb, ++it) {
           const int s = it % STAGES;
           const uint32_t ph = (it / STAGES) & 1;
           mbar_wait(&empty[s], ph ^ 1);
-          mbar_arrive_expect_tx(&full[s], A_STAGE + B_STAGE);
+          if (CG == 1 || leader) mbar_arrive_expect_tx(&full[s], CG * (A_STAGE + B_STAGE));
           uint8_t* a = sA + s * A_STAGE;
           uint8_t* b = sB + s * B_STAGE;
           const int k0 = kb * BK;
           if (!A_T) {
-            tma_load_2d(a, &tmA, &full[s], k0, m0);  // box {64 k, 128 m}
+            load(a, &tmA, &full[s], k0, m0);  // box {64 k, 128 m}
           } else {
 #pragma unroll
-            for (int c = 0; c < BM / 64; ++c) tma_load_2d(a + c * 8192, &tmA, &full[s], m0 + 64 * c, k0);  // box {64 m, 64 k}
+            for (int c = 0; c < BM / 64; ++c) load(a + c * 8192, &tmA, &full[s], m0 + 64 * c, k0);  // box {64 m, 64 k}
           }
           if (!B_T) {
-            tma_load_2d(b, &tmB, &full[s], k0, n0);  // box {64 k, 256 n}
+            load(b, &tmB, &full[s], k0, n0);  // box {64 k, 256 / CG n}
           } else {
 #pragma unroll
-            for (int c = 0; c < BN / 64; ++c) tma_load_2d(b + c * 8192, &tmB, &full[s], n0 + 64 * c, k0);  // box {64 n, 64 k}
+            for (int c = 0; c < B_ROWS / 64; ++c) load(b + c * 8192, &tmB, &full[s], n0 + 64 * c, k0);  // box {64 n, 64 k}
           }
+          // the follower's arrival carries no data ordering (its bytes are counted by complete_tx): relaxed, after the loads
+          if (CG == 2 && !leader) mbar_arrive_cluster_relaxed(&full[s], 0);
         }
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc_bf16(BM, BN, A_T ? 1 : 0, B_T ? 1 : 0);
+    if (lane == 0 && leader) {
+      constexpr uint32_t idesc = make_idesc_bf16(BM * CG, BN, A_T ? 1 : 0, B_T ? 1 : 0);
       uint32_t it = 0, t = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++t) {
+      for (int tile = unit; tile < total_tiles; tile += n_units, ++t) {
         const uint32_t buf = t & 1, aph = (t >> 1) & 1;
         mbar_wait(&tempty[buf], aph ^ 1);
         tc_fence_after();
@@ -124,22 +147,26 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           for (int k = 0; k < BK / 16; ++k) {
             const uint64_t adesc = A_T ? make_sdesc_sw128(a_addr + k * 2048, 8192, 1024) : make_sdesc_sw128(a_addr + k * 32, 16, 1024);
             const uint64_t bdesc = B_T ? make_sdesc_sw128(b_addr + k * 2048, 8192, 1024) : make_sdesc_sw128(b_addr + k * 32, 16, 1024);
-            umma_ss(d_tmem, adesc, bdesc, idesc, (kb | k) != 0 ? 1u : 0u);
+            if (CG == 2) umma_ss_cg2(d_tmem, adesc, bdesc, idesc, (kb | k) != 0 ? 1u : 0u);
+            else umma_ss(d_tmem, adesc, bdesc, idesc, (kb | k) != 0 ? 1u : 0u);
           }
-          umma_commit(&empty[s]);  // frees the smem stage once these MMAs have read it
+          // frees the smem stage (in both CTAs of a pair) once these MMAs have read it
+          if (CG == 2) umma_commit_mc2(&empty[s], 3);
+          else umma_commit(&empty[s]);
         }
-        umma_commit(&tfull[buf]);  // accumulator complete
+        if (CG == 2) umma_commit_mc2(&tfull[buf], 3);  // accumulator complete (both CTAs' epilogues)
+        else umma_commit(&tfull[buf]);
       }
     }
   } else {
     // ---------------- epilogue: thread = one accumulator row ----------------
     const int quad = warp & 3;  // TMEM lane quadrant this warp may access
     uint32_t t = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++t) {
+    for (int tile = unit; tile < total_tiles; tile += n_units, ++t) {
       int m_blk, n_blk;
       tile_coords(tile, p.tiles_m, p.tiles_n, m_blk, n_blk);
       const uint32_t buf = t & 1, aph = (t >> 1) & 1;
-      const int row = m_blk * BM + quad * 32 + lane;
+      const int row = (m_blk * CG + cta_rank) * BM + quad * 32 + lane;
       const bool row_ok = row < p.M;
       if ((p.epi == PRFL_EPI_RESIDUAL || (p.epi == PRFL_EPI_F32 && p.beta)) && row_ok) {
         // the read-modify-write epilogue is latency-bound on the fp32 tile it updates: pull this thread's row segment
@@ -258,33 +285,64 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&tempty[buf]);
+      if (lane == 0) {
+        if (CG == 2) mbar_arrive_cluster(&tempty[buf], 0);
+        else mbar_arrive(&tempty[buf]);
+      }
     }
   }
 
   tc_fence_before();
-  __syncthreads();
+  __syncwarp();
+  if (CG == 2) cluster_sync_all();   // the peer may still be the target of multicast commits / hold live accumulators
+  else __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc<512>(tmem_base);
+    if (CG == 2) tmem_dealloc_cg2<512>(tmem_base);
+    else tmem_dealloc<512>(tmem_base);
   }
 }
 
-template <bool A_T, bool B_T>
+template <bool A_T, bool B_T, int CG>
 static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, cudaStream_t st) {
   static bool attr_set = false;
-  auto kern = gemm_bf16_kernel<A_T, B_T>;
+  auto kern = gemm_bf16_kernel<A_T, B_T, CG>;
+  constexpr int SMEM = GemmCfg<CG>::SMEM;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM);
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
     if (e != cudaSuccess) return cuda_fail(e, "gemm: cudaFuncSetAttribute");
     attr_set = true;
   }
-  int total = p.tiles_m * p.tiles_n;
-  int grid = total < sm_count() ? total : sm_count();
-  kern<<<grid, GEMM_THREADS, GEMM_SMEM, st>>>(tmA, tmB, p);
+  const int total = p.tiles_m * p.tiles_n;          // tiles_m counts (128 * CG)-row tiles
+  const int units = sm_count() / CG;
+  const int grid = (total < units ? total : units) * CG;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(GEMM_THREADS);
+  cfg.dynamicSmemBytes = SMEM;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CG;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, tmA, tmB, p);
   count_launch();
+  if (e != cudaSuccess) return cuda_fail(e, "gemm_bf16 launch");
   PRFL_LAUNCH_CHECK("gemm_bf16");
   return PRFL_OK;
+}
+
+// PRFL_GEMM_CG=1 forces the single-CTA kernel (debugging / A-B comparison); default is the CTA-pair kernel when M > 128.
+static int gemm_cta_group(int M) {
+  static int forced = [] {
+    const char* e = getenv("PRFL_GEMM_CG");
+    return e ? atoi(e) : 0;
+  }();
+  if (forced == 1 || forced == 2) return forced;
+  return M > BM ? 2 : 1;
 }
 
 }  // namespace prfl
@@ -307,21 +365,28 @@ extern "C" int prfl_gemm_bf16(const void* A, int64_t lda, int a_trans, const voi
                    (reinterpret_cast<uintptr_t>(gate) & 15) == 0 && (reinterpret_cast<uintptr_t>(aux_bf16) & 15) == 0 &&
                    ((epi == PRFL_EPI_F32 || epi == PRFL_EPI_RESIDUAL) ? true : ldc % 8 == 0),
                PRFL_E_ALIGN, "gemm: out/bias/gate/aux must be 16-byte aligned");
+  const int cg = gemm_cta_group(M);
   CUtensorMap tmA, tmB;
   int rc;
   if (!a_trans) rc = make_tmap_2d(&tmA, A, (uint64_t)K, (uint64_t)M, (uint64_t)lda * 2, 64, BM, 1);
   else rc = make_tmap_2d(&tmA, A, (uint64_t)M, (uint64_t)K, (uint64_t)lda * 2, 64, 64, 1);
   if (rc != PRFL_OK) return rc;
-  if (!b_trans) rc = make_tmap_2d(&tmB, B, (uint64_t)K, (uint64_t)N, (uint64_t)ldb * 2, 64, BN, 1);
+  if (!b_trans) rc = make_tmap_2d(&tmB, B, (uint64_t)K, (uint64_t)N, (uint64_t)ldb * 2, 64, BN / cg, 1);
   else rc = make_tmap_2d(&tmB, B, (uint64_t)N, (uint64_t)K, (uint64_t)ldb * 2, 64, 64, 1);
   if (rc != PRFL_OK) return rc;
   GemmParams p;
   p.out = out; p.ldc = ldc; p.bias = bias; p.gate = gate; p.aux = (__nv_bfloat16*)aux_bf16; p.ldaux = ldaux;
   p.M = M; p.N = N; p.K = K; p.epi = epi; p.beta = beta;
-  p.tiles_m = (M + BM - 1) / BM; p.tiles_n = (N + BN - 1) / BN; p.num_kb = (K + BK - 1) / BK;
+  p.tiles_m = (M + BM * cg - 1) / (BM * cg); p.tiles_n = (N + BN - 1) / BN; p.num_kb = (K + BK - 1) / BK;
   cudaStream_t st = (cudaStream_t)stream;
-  if (!a_trans && !b_trans) return launch_gemm<false, false>(tmA, tmB, p, st);
-  if (!a_trans && b_trans) return launch_gemm<false, true>(tmA, tmB, p, st);
-  if (a_trans && !b_trans) return launch_gemm<true, false>(tmA, tmB, p, st);
-  return launch_gemm<true, true>(tmA, tmB, p, st);
+  if (cg == 2) {
+    if (!a_trans && !b_trans) return launch_gemm<false, false, 2>(tmA, tmB, p, st);
+    if (!a_trans && b_trans) return launch_gemm<false, true, 2>(tmA, tmB, p, st);
+    if (a_trans && !b_trans) return launch_gemm<true, false, 2>(tmA, tmB, p, st);
+    return launch_gemm<true, true, 2>(tmA, tmB, p, st);
+  }
+  if (!a_trans && !b_trans) return launch_gemm<false, false, 1>(tmA, tmB, p, st);
+  if (!a_trans && b_trans) return launch_gemm<false, true, 1>(tmA, tmB, p, st);
+  if (a_trans && !b_trans) return launch_gemm<true, false, 1>(tmA, tmB, p, st);
+  return launch_gemm<true, true, 1>(tmA, tmB, p, st);
 }
