@@ -1,6 +1,6 @@
 // Flash-attention backward for sm_100a (bf16, head_dim 128, non-causal, ragged tails), tcgen05 + TMEM + TMA.
-// Two kernels, both with the forward kernel's skeleton (TMA warp, MMA warp, 2 x 128 softmax threads that
-// ping-pong over 64-wide sub-tiles), no atomics, deterministic:
+// Two kernels, both with the forward kernel's skeleton (TMA warp, MMA warp, 2 x 256 softmax-gradient threads — two
+// threads per row — that ping-pong over 64-wide sub-tiles), no atomics, deterministic:
 //
 //   attn_bwd_dkdv_kernel : CTA = one head x 128 keys (K_j, V_j resident in smem), loop over 64-query sub-tiles
 //        S^T = K Q^T, dP^T = V dO^T           (SS MMA, M = keys, N = 64 queries)       -> TMEM
@@ -19,7 +19,8 @@
 
 namespace prfl {
 
-constexpr int BWD_THREADS = 320;
+constexpr int BWD_THREADS = 576;            // 16 softmax-gradient warps (2 threads per row) + TMA warp + MMA warp
+constexpr int W_TMA = 16, W_MMA = 17;
 constexpr int BIG = 128;                     // resident tile rows
 constexpr int SUB = 64;                      // streamed sub-tile rows
 constexpr int BIG_BYTES = BIG * 128 * 2;     // 32 KB
@@ -83,7 +84,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmR0, const __grid_constant_
   const int L_stream = DKDV ? p.Lq : p.Lk;
   const int n_sub = (L_stream + SUB - 1) / SUB;
 
-  if (warp == 8 && lane == 0) {
+  if (warp == W_TMA && lane == 0) {
     tma_prefetch_desc(&tmR0);
     tma_prefetch_desc(&tmR1);
     tma_prefetch_desc(&tmS0);
@@ -95,20 +96,20 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmR0, const __grid_constant_
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(&xfull[b], 1);
-      mbar_init(&pfull[b], 4);
+      mbar_init(&pfull[b], 8);
     }
     mbar_init(ofull, 1);
     fence_barrier_init();
   }
-  if (warp == 9) tmem_alloc<512>(tmem_slot);
+  if (warp == W_MMA) tmem_alloc<512>(tmem_slot);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp == 8) {
+  if (warp == W_TMA) {
     // ------------------------------- TMA producer -------------------------------
-    if (lane == 0) {
+    if (elect_one()) {
       mbar_arrive_expect_tx(rfull, 2 * BIG_BYTES);
 #pragma unroll
       for (int c = 0; c < 2; ++c) {
@@ -127,46 +128,51 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmR0, const __grid_constant_
         }
       }
     }
-  } else if (warp == 9) {
+  } else if (warp == W_MMA) {
     // ------------------------------- MMA issuer -------------------------------
-    if (lane == 0) {
+    if (elect_one()) {
       constexpr uint32_t idesc_x = make_idesc_bf16(128, SUB, 0, 0);   // [128 x 64] = R (K-major) x S^T (K-major)
       constexpr uint32_t idesc_acc = make_idesc_bf16(128, 128, 0, 1); // [128 x 128] += tmem A x MN-major B
       const uint32_t r0a = smem_u32(sR0), r1a = smem_u32(sR1), s0a = smem_u32(sS0), s1a = smem_u32(sS1);
+      constexpr uint32_t HI = sdesc_hi(1024);
       auto issue_x = [&](int b, int st) {
         // X_b = R0 . S0^T ; Y_b = R1 . S1^T   (contraction over head_dim = 128, 8 k-steps)
+        const uint32_t r0lo = sdesc_lo(r0a, 16), r1lo = sdesc_lo(r1a, 16);
+        const uint32_t s0lo = sdesc_lo(s0a + st * SUB_BYTES, 16), s1lo = sdesc_lo(s1a + st * SUB_BYTES, 16);
+        const uint32_t dx = tmem_base + b * 64, dy = tmem_base + 128 + b * 64;
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
-          const uint32_t offr = (k >> 2) * 16384 + (k & 3) * 32, offs = (k >> 2) * 8192 + (k & 3) * 32;
-          umma_ss(tmem_base + b * 64, make_sdesc_sw128(r0a + offr, 16, 1024), make_sdesc_sw128(s0a + st * SUB_BYTES + offs, 16, 1024),
-                  idesc_x, k != 0 ? 1u : 0u);
+          const uint32_t offr = (k >> 2) * (16384 >> 4) + (k & 3) * 2, offs = (k >> 2) * (8192 >> 4) + (k & 3) * 2;
+          umma_ss(dx, sdesc_join(r0lo + offr, HI), sdesc_join(s0lo + offs, HI), idesc_x, k != 0 ? 1u : 0u);
         }
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
-          const uint32_t offr = (k >> 2) * 16384 + (k & 3) * 32, offs = (k >> 2) * 8192 + (k & 3) * 32;
-          umma_ss(tmem_base + 128 + b * 64, make_sdesc_sw128(r1a + offr, 16, 1024),
-                  make_sdesc_sw128(s1a + st * SUB_BYTES + offs, 16, 1024), idesc_x, k != 0 ? 1u : 0u);
+          const uint32_t offr = (k >> 2) * (16384 >> 4) + (k & 3) * 2, offs = (k >> 2) * (8192 >> 4) + (k & 3) * 2;
+          umma_ss(dy, sdesc_join(r1lo + offr, HI), sdesc_join(s1lo + offs, HI), idesc_x, k != 0 ? 1u : 0u);
         }
         umma_commit(&xfull[b]);
       };
       auto issue_acc = [&](int b, int st, bool acc) {
-        // contraction over the 64 streamed rows (4 k-steps); B = streamed tile as MN-major operand
+        // contraction over the 64 streamed rows (4 k-steps); B = streamed tile as MN-major operand (LBO = 8192).
+        // packed bf16 A columns of streamed rows 16k..16k+15 live at 32*(k>>1) + 8*(k&1) of the buffer
+        const uint32_t s0lo = sdesc_lo(s0a + st * SUB_BYTES, 8192), s1lo = sdesc_lo(s1a + st * SUB_BYTES, 8192);
+        const uint32_t ax = tmem_base + b * 64, ay = tmem_base + 128 + b * 64;
         if (DKDV) {
           // dV (ACC0) += P^T_b . dO ; dK (ACC1) += dS^T_b . Q
 #pragma unroll
           for (int k = 0; k < 4; ++k)
-            umma_ts(tmem_base + 256, tmem_base + b * 64 + k * 8, make_sdesc_sw128(s1a + st * SUB_BYTES + k * 2048, 8192, 1024),
-                    idesc_acc, (acc || k != 0) ? 1u : 0u);
+            umma_ts(tmem_base + 256, ax + (k >> 1) * 32 + (k & 1) * 8, sdesc_join(s1lo + k * (2048 >> 4), HI), idesc_acc,
+                    (acc || k != 0) ? 1u : 0u);
 #pragma unroll
           for (int k = 0; k < 4; ++k)
-            umma_ts(tmem_base + 384, tmem_base + 128 + b * 64 + k * 8, make_sdesc_sw128(s0a + st * SUB_BYTES + k * 2048, 8192, 1024),
-                    idesc_acc, (acc || k != 0) ? 1u : 0u);
+            umma_ts(tmem_base + 384, ay + (k >> 1) * 32 + (k & 1) * 8, sdesc_join(s0lo + k * (2048 >> 4), HI), idesc_acc,
+                    (acc || k != 0) ? 1u : 0u);
         } else {
           // dQ (ACC0) += dS_b . K
 #pragma unroll
           for (int k = 0; k < 4; ++k)
-            umma_ts(tmem_base + 256, tmem_base + 128 + b * 64 + k * 8, make_sdesc_sw128(s0a + st * SUB_BYTES + k * 2048, 8192, 1024),
-                    idesc_acc, (acc || k != 0) ? 1u : 0u);
+            umma_ts(tmem_base + 256, ay + (k >> 1) * 32 + (k & 1) * 8, sdesc_join(s0lo + k * (2048 >> 4), HI), idesc_acc,
+                    (acc || k != 0) ? 1u : 0u);
         }
       };
       mbar_wait(rfull, 0);
@@ -190,7 +196,13 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmR0, const __grid_constant_
     }
   } else {
     // ------------------------------- softmax-gradient warps + epilogue -------------------------------
-    const int wg = warp >> 2;       // handles sub-tiles i with (i & 1) == wg
+    // 16 warps: buffer `wg` = warp / 8 handles sub-tiles i with (i & 1) == wg; inside a buffer two warps share each TMEM
+    // lane quadrant and split the 64 streamed columns (`half`): two threads per row halve the latency of this stage,
+    // which is what bounds the tensor pipe here (the MMAs of one buffer overlap the softmax-gradient of the other).
+    // Packed bf16 results of fp32 columns [32h + 16c, +16) go to columns [32h + 8c, +8): they only alias fp32 columns the
+    // same thread has already consumed, so the two halves never race.
+    const int wg = warp >> 3;
+    const int half = (warp >> 2) & 1;
     const int quad = warp & 3;
     const int row = r0 + quad * 32 + lane;               // resident row of this thread (key | query)
     const uint32_t lane_off = (uint32_t)(quad * 32) << 16;
@@ -201,33 +213,37 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmR0, const __grid_constant_
       delta_row = ok ? p.delta[(int64_t)head * p.Lq + row] : 0.f;
     }
     float* ld = sLD + wg * 2 * SUB;
-    const int tid_wg = threadIdx.x & 127;
+    const int tid_wg = threadIdx.x & 255;
+    const int c0 = half * 32;                            // this thread's 32 fp32 columns of every sub-tile
     for (int i = wg; i < n_sub; i += 2) {
       if (DKDV) {
         // stage lse*log2e and delta of the 64 streamed queries (guarding the ragged tail)
-        named_bar_sync(1 + wg, 128);                       // previous sub-tile's readers are done
-        const int qi = i * SUB + (tid_wg & 63);
-        const bool ok = qi < p.Lq;
-        if (tid_wg < 64) ld[tid_wg] = ok ? p.lse[(int64_t)head * p.Lq + qi] * 1.4426950408889634f : INFINITY;
-        else ld[tid_wg] = ok ? p.delta[(int64_t)head * p.Lq + qi] : 0.f;
-        named_bar_sync(1 + wg, 128);
+        named_bar_sync(1 + wg, 256);                       // previous sub-tile's readers are done
+        if (tid_wg < 128) {
+          const int qi = i * SUB + (tid_wg & 63);
+          const bool ok = qi < p.Lq;
+          if (tid_wg < 64) ld[tid_wg] = ok ? p.lse[(int64_t)head * p.Lq + qi] * 1.4426950408889634f : INFINITY;
+          else ld[tid_wg] = ok ? p.delta[(int64_t)head * p.Lq + qi] : 0.f;
+        }
+        named_bar_sync(1 + wg, 256);
       }
       mbar_wait(&xfull[wg], (i >> 1) & 1);
       tc_fence_after();
-      const uint32_t x_addr = tmem_base + wg * 64 + lane_off, y_addr = tmem_base + 128 + wg * 64 + lane_off;
+      const uint32_t x_addr = tmem_base + wg * 64 + c0 + lane_off, y_addr = tmem_base + 128 + wg * 64 + c0 + lane_off;
 #pragma unroll
       for (int c = 0; c < 2; ++c) {
-        uint32_t xs[32], ys[32];
-        tmem_ld32(x_addr + c * 32, xs);
-        tmem_ld32(y_addr + c * 32, ys);
+        uint32_t xs[16], ys[16];
+        tmem_ld16(x_addr + c * 16, xs);
+        tmem_ld16(y_addr + c * 16, ys);
         tmem_wait_ld();
-        uint32_t pk[16], dk[16];
+        uint32_t pk[8], dk[8];
 #pragma unroll
-        for (int j = 0; j < 32; j += 2) {
+        for (int j = 0; j < 16; j += 2) {
           float l0, l1, d0, d1;
           if (DKDV) {
-            l0 = ld[c * 32 + j]; l1 = ld[c * 32 + j + 1];
-            d0 = ld[SUB + c * 32 + j]; d1 = ld[SUB + c * 32 + j + 1];
+            const float2 l2 = *reinterpret_cast<const float2*>(ld + c0 + c * 16 + j);
+            const float2 d2 = *reinterpret_cast<const float2*>(ld + SUB + c0 + c * 16 + j);
+            l0 = l2.x; l1 = l2.y; d0 = d2.x; d1 = d2.y;
           } else {
             l0 = l1 = lse2_row; d0 = d1 = delta_row;
           }
@@ -239,72 +255,50 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmR0, const __grid_constant_
           pk[j >> 1] = pack_bf16x2(p0, p1);
           dk[j >> 1] = pack_bf16x2(g0, g1);
         }
-        // packed columns [16c, 16c+16) only overlap fp32 columns this thread has already consumed
-        if (DKDV) tmem_st16(x_addr + c * 16, pk);   // P^T (A operand of the dV MMA)
-        tmem_st16(y_addr + c * 16, dk);             // dS^T | dS (A operand of the dK | dQ MMA)
+        if (DKDV) tmem_st8(x_addr + c * 8, pk);   // P^T (A operand of the dV MMA)
+        tmem_st8(y_addr + c * 8, dk);             // dS^T | dS (A operand of the dK | dQ MMA)
       }
       tmem_wait_st();
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&pfull[wg]);
     }
-    // ---- epilogue ----
+    // ---- epilogue: 16 warps share the accumulator read-out ----
     mbar_wait(ofull, 0);
     tc_fence_after();
     const int L_res = DKDV ? p.Lk : p.Lq;
     const bool row_ok = row < L_res;
-    if (DKDV) {
-      // wg 0 stores dV (ACC0), wg 1 stores dK = scale * ACC1
-      const uint32_t a_addr = tmem_base + 256 + wg * 128 + lane_off;
-      __nv_bfloat16* dst = wg == 0 ? p.out1 + (int64_t)row * p.o1_ld_tok + (int64_t)head * p.o1_ld_head
-                                   : p.out0 + (int64_t)row * p.o0_ld_tok + (int64_t)head * p.o0_ld_head;
-      const float mul = wg == 0 ? 1.0f : p.scale;
+    // DKDV: buffer group 0 stores dV (ACC0), group 1 stores dK = scale * ACC1; each half takes 64 of the 128 columns.
+    // DQ  : the four (group, half) pairs take 32 columns each of dQ (ACC0).
+    const int ncol = DKDV ? 64 : 32;
+    const int col0 = DKDV ? half * 64 : (wg * 2 + half) * 32;
+    const uint32_t a_addr = tmem_base + 256 + (DKDV ? wg * 128 : 0) + col0 + lane_off;
+    __nv_bfloat16* dst = (DKDV && wg == 0) ? p.out1 + (int64_t)row * p.o1_ld_tok + (int64_t)head * p.o1_ld_head + col0
+                                           : p.out0 + (int64_t)row * p.o0_ld_tok + (int64_t)head * p.o0_ld_head + col0;
+    const float mul = (DKDV && wg == 1) ? p.scale : 1.0f;
 #pragma unroll 1
-      for (int c = 0; c < 4; ++c) {
-        uint32_t o[32];
-        tmem_ld32(a_addr + c * 32, o);
-        tmem_wait_ld();
-        if (row_ok) {
+    for (int c = 0; c < ncol / 16; ++c) {
+      uint32_t o[16];
+      tmem_ld16(a_addr + c * 16, o);
+      tmem_wait_ld();
+      if (row_ok) {
 #pragma unroll
-          for (int j = 0; j < 32; j += 8) {
-            uint4 v;
-            v.x = pack_bf16x2(__uint_as_float(o[j]) * mul, __uint_as_float(o[j + 1]) * mul);
-            v.y = pack_bf16x2(__uint_as_float(o[j + 2]) * mul, __uint_as_float(o[j + 3]) * mul);
-            v.z = pack_bf16x2(__uint_as_float(o[j + 4]) * mul, __uint_as_float(o[j + 5]) * mul);
-            v.w = pack_bf16x2(__uint_as_float(o[j + 6]) * mul, __uint_as_float(o[j + 7]) * mul);
-            *reinterpret_cast<uint4*>(dst + c * 32 + j) = v;
-          }
+        for (int j = 0; j < 16; j += 8) {
+          uint4 v;
+          v.x = pack_bf16x2(__uint_as_float(o[j]) * mul, __uint_as_float(o[j + 1]) * mul);
+          v.y = pack_bf16x2(__uint_as_float(o[j + 2]) * mul, __uint_as_float(o[j + 3]) * mul);
+          v.z = pack_bf16x2(__uint_as_float(o[j + 4]) * mul, __uint_as_float(o[j + 5]) * mul);
+          v.w = pack_bf16x2(__uint_as_float(o[j + 6]) * mul, __uint_as_float(o[j + 7]) * mul);
+          *reinterpret_cast<uint4*>(dst + c * 16 + j) = v;
         }
-        __syncwarp();
       }
-    } else {
-      // both warpgroups store dQ (ACC0): wg 0 columns [0,64), wg 1 columns [64,128)
-      const uint32_t a_addr = tmem_base + 256 + wg * 64 + lane_off;
-      __nv_bfloat16* dst = p.out0 + (int64_t)row * p.o0_ld_tok + (int64_t)head * p.o0_ld_head + wg * 64;
-#pragma unroll 1
-      for (int c = 0; c < 2; ++c) {
-        uint32_t o[32];
-        tmem_ld32(a_addr + c * 32, o);
-        tmem_wait_ld();
-        if (row_ok) {
-#pragma unroll
-          for (int j = 0; j < 32; j += 8) {
-            uint4 v;
-            v.x = pack_bf16x2(__uint_as_float(o[j]), __uint_as_float(o[j + 1]));
-            v.y = pack_bf16x2(__uint_as_float(o[j + 2]), __uint_as_float(o[j + 3]));
-            v.z = pack_bf16x2(__uint_as_float(o[j + 4]), __uint_as_float(o[j + 5]));
-            v.w = pack_bf16x2(__uint_as_float(o[j + 6]), __uint_as_float(o[j + 7]));
-            *reinterpret_cast<uint4*>(dst + c * 32 + j) = v;
-          }
-        }
-        __syncwarp();
-      }
+      __syncwarp();
     }
   }
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 9) {
+  if (warp == W_MMA) {
     tc_fence_after();
     tmem_dealloc<512>(tmem_base);
   }

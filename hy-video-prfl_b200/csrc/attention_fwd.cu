@@ -83,7 +83,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
 
   if (warp == 8) {
     // ------------------------------- TMA producer -------------------------------
-    if (lane == 0) {
+    if (elect_one()) {
       mbar_arrive_expect_tx(qfull, 2 * TILE_BYTES);
 #pragma unroll
       for (int t = 0; t < 2; ++t)
@@ -104,26 +104,27 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     }
   } else if (warp == 9) {
     // ------------------------------- MMA issuer -------------------------------
-    if (lane == 0) {
+    if (elect_one()) {
       constexpr uint32_t idesc_qk = make_idesc_bf16(128, 128, 0, 0);
       constexpr uint32_t idesc_pv = make_idesc_bf16(128, 128, 0, 1);  // A = P (TMEM, K-major), B = V (MN-major)
       const uint32_t q_addr = smem_u32(sQ), k_addr = smem_u32(sK), v_addr = smem_u32(sV);
+      constexpr uint32_t HI = sdesc_hi(1024);
       auto issue_qk = [&](int t, int ks) {
-        const uint32_t qa = q_addr + t * TILE_BYTES, ka = k_addr + ks * TILE_BYTES;
+        const uint32_t qlo = sdesc_lo(q_addr + t * TILE_BYTES, 16), klo = sdesc_lo(k_addr + ks * TILE_BYTES, 16);
+        const uint32_t d = tmem_base + t * 128;
 #pragma unroll
         for (int k = 0; k < HD / 16; ++k) {
-          const uint32_t off = (k >> 2) * 16384 + (k & 3) * 32;
-          umma_ss(tmem_base + t * 128, make_sdesc_sw128(qa + off, 16, 1024), make_sdesc_sw128(ka + off, 16, 1024), idesc_qk,
-                  k != 0 ? 1u : 0u);
+          const uint32_t off = (k >> 2) * (16384 >> 4) + (k & 3) * (32 >> 4);   // in 16-byte units
+          umma_ss(d, sdesc_join(qlo + off, HI), sdesc_join(klo + off, HI), idesc_qk, k != 0 ? 1u : 0u);
         }
         umma_commit(&sfull[t]);
       };
       auto issue_pv = [&](int t, int vs, bool acc) {
-        const uint32_t va = v_addr + vs * TILE_BYTES;
+        const uint32_t vlo = sdesc_lo(v_addr + vs * TILE_BYTES, 16384);
+        const uint32_t d = tmem_base + 256 + t * 128, a = tmem_base + t * 128;
 #pragma unroll
         for (int k = 0; k < KT / 16; ++k)
-          umma_ts(tmem_base + 256 + t * 128, tmem_base + t * 128 + k * 8, make_sdesc_sw128(va + k * 2048, 16384, 1024), idesc_pv,
-                  (acc || k != 0) ? 1u : 0u);
+          umma_ts(d, a + k * 8, sdesc_join(vlo + k * (2048 >> 4), HI), idesc_pv, (acc || k != 0) ? 1u : 0u);
       };
       mbar_wait(qfull, 0);
       mbar_wait(&kfull[0], 0);

@@ -92,7 +92,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
-    if (lane == 0) {
+    if (elect_one()) {
       uint32_t it = 0;
       auto load = [&](void* dst, const CUtensorMap* tm, uint64_t* bar, int c0, int c1) {
         if (CG == 2) tma_load_2d_cg2(dst, tm, bar, c0, c1);   // bytes are credited to the leader CTA's barrier
@@ -128,7 +128,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       }
     }
   } else if (warp == 1) {
-    if (lane == 0 && leader) {
+    if (leader && elect_one()) {
       constexpr uint32_t idesc = make_idesc_bf16(BM * CG, BN, A_T ? 1 : 0, B_T ? 1 : 0);
       uint32_t it = 0, t = 0;
       for (int tile = unit; tile < total_tiles; tile += n_units, ++t) {
