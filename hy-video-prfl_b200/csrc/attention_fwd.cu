@@ -6,8 +6,8 @@
 // tile A's MMAs the softmax warps of tile B run, as in FlashAttention-4).  O is rescaled lazily: the
 // running max used for exp2 only moves when the true max grew by more than 8 (log2 units), which is
 // exact because the row sum is kept relative to the same stale max.
-// Warps: 0-3 softmax of Q tile 0, 4-7 softmax of Q tile 1, 8 TMA producer, 9 MMA issuer.
-// TMEM: S0 [0,128) S1 [128,256) O0 [256,384) O1 [384,512); P_i aliases the first 64 columns of S_i.
+// Warps: 0-7 softmax of Q tile 0, 8-15 softmax of Q tile 1 (two threads per row), 16 TMA producer, 17 MMA issuer.
+// TMEM: S0 [0,128) S1 [128,256) O0 [256,384) O1 [384,512); P_i (bf16) aliases columns [0,32) and [64,96) of S_i.
 // Roofline: tensor pipe, 4*Lq*Lk*128 flops per head.
 #include <math.h>
 
@@ -15,13 +15,15 @@
 
 namespace prfl {
 
-constexpr int ATT_THREADS = 320;
+constexpr int ATT_THREADS = 576;   // 16 softmax warps (2 Q tiles x 2 column halves x 4 lane quadrants) + TMA warp + MMA warp
+constexpr int AW_TMA = 16, AW_MMA = 17;
 constexpr int QT = 128;       // rows per Q tile
 constexpr int KT = 128;       // keys per KV tile
 constexpr int HD = 128;
 constexpr int TILE_BYTES = 128 * 128 * 2;  // 32 KB: any 128 x 128 bf16 tile (two 64-wide TMA boxes)
 constexpr int KV_STAGES = 2;
-constexpr int ATT_SMEM = 2 * TILE_BYTES + 2 * KV_STAGES * TILE_BYTES + 256 + 1024;
+constexpr int ATT_XCH = 2 * 2 * 2 * 128 * 4;   // [slot][Q tile][half][row] floats exchanged between the two threads of a row
+constexpr int ATT_SMEM = 2 * TILE_BYTES + 2 * KV_STAGES * TILE_BYTES + ATT_XCH + 256 + 1024;
 
 struct AttnFwdParams {
   __nv_bfloat16* o;
@@ -43,7 +45,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   uint8_t* sQ = smem;                                  // [2][32 KB]
   uint8_t* sK = smem + 2 * TILE_BYTES;                 // [KV_STAGES][32 KB]
   uint8_t* sV = sK + KV_STAGES * TILE_BYTES;           // [KV_STAGES][32 KB]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sV + KV_STAGES * TILE_BYTES);
+  float* sX = reinterpret_cast<float*>(sV + KV_STAGES * TILE_BYTES);   // [2 slots][2 tiles][2 halves][128]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(sX) + ATT_XCH);
   uint64_t* qfull = bars;          // [1]
   uint64_t* kfull = bars + 1;      // [2]
   uint64_t* kempty = bars + 3;     // [2]
@@ -59,7 +62,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   const int q0 = blockIdx.x * (2 * QT);
   const int n_kv = (p.Lk + KT - 1) / KT;
 
-  if (warp == 8 && lane == 0) {
+  if (warp == AW_TMA && lane == 0) {
     tma_prefetch_desc(&tmQ);
     tma_prefetch_desc(&tmK);
     tma_prefetch_desc(&tmV);
@@ -70,18 +73,18 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       mbar_init(&vfull[s], 1);
       mbar_init(&vempty[s], 1);
       mbar_init(&sfull[s], 1);
-      mbar_init(&pfull[s], 4);
+      mbar_init(&pfull[s], 8);
     }
     mbar_init(ofull, 1);
     fence_barrier_init();
   }
-  if (warp == 9) tmem_alloc<512>(tmem_slot);
+  if (warp == AW_MMA) tmem_alloc<512>(tmem_slot);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp == 8) {
+  if (warp == AW_TMA) {
     // ------------------------------- TMA producer -------------------------------
     if (elect_one()) {
       mbar_arrive_expect_tx(qfull, 2 * TILE_BYTES);
@@ -102,7 +105,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         for (int c = 0; c < 2; ++c) tma_load_3d(sV + s * TILE_BYTES + c * 16384, &tmV, &vfull[s], c * 64, j * KT, head);
       }
     }
-  } else if (warp == 9) {
+  } else if (warp == AW_MMA) {
     // ------------------------------- MMA issuer -------------------------------
     if (elect_one()) {
       constexpr uint32_t idesc_qk = make_idesc_bf16(128, 128, 0, 0);
@@ -124,7 +127,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         const uint32_t d = tmem_base + 256 + t * 128, a = tmem_base + t * 128;
 #pragma unroll
         for (int k = 0; k < KT / 16; ++k)
-          umma_ts(d, a + k * 8, sdesc_join(vlo + k * (2048 >> 4), HI), idesc_pv, (acc || k != 0) ? 1u : 0u);
+          umma_ts(d, a + (k >> 2) * 64 + (k & 3) * 8, sdesc_join(vlo + k * (2048 >> 4), HI), idesc_pv, (acc || k != 0) ? 1u : 0u);
       };
       mbar_wait(qfull, 0);
       mbar_wait(&kfull[0], 0);
@@ -160,92 +163,94 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     }
   } else {
     // ------------------------------- softmax + epilogue -------------------------------
-    const int t = warp >> 2;        // Q tile handled by this warpgroup
-    const int quad = warp & 3;      // TMEM lane quadrant
-    const int row = q0 + t * QT + quad * 32 + lane;
+    // Two threads per query row: warp = (Q tile t, column half h, lane quadrant); thread (h, row) owns keys
+    // [64h, 64h + 64) of every KV tile and columns [64h, 64h + 64) of O.  The tensor pipe waits on exactly this stage
+    // (P_t(j) must exist 1024 tensor-cycles after S_t(j)), so its latency, not its throughput, is what matters.
+    // The two threads of a row agree on the running max through shared memory (one 256-thread named barrier per tile).
+    // Packed bf16 P of keys [64h, 64h+64) goes to TMEM columns [64h, 64h+32): it only aliases fp32 S columns that the
+    // same thread has already consumed.
+    const int t = warp >> 3;                 // Q tile
+    const int half = (warp >> 2) & 1;        // which 64 keys / 64 output columns
+    const int quad = warp & 3;               // TMEM lane quadrant
+    const int r = quad * 32 + lane;          // row inside the Q tile
+    const int row = q0 + t * QT + r;
     const uint32_t lane_off = (uint32_t)(quad * 32) << 16;
-    const uint32_t s_addr = tmem_base + t * 128 + lane_off;
-    const uint32_t o_addr = tmem_base + 256 + t * 128 + lane_off;
-    float m_used = -INFINITY;  // max the exponentials are currently relative to (log2 domain)
-    float l_sum = 0.f;
+    const uint32_t s_addr = tmem_base + t * 128 + half * 64 + lane_off;
+    const uint32_t o_addr = tmem_base + 256 + t * 128 + half * 64 + lane_off;
+    float* x_mine = sX + (t * 2 + half) * 128 + r;          // + slot * 512: exchange slots alternate per tile
+    float* x_peer = sX + (t * 2 + (half ^ 1)) * 128 + r;
+    float m_used = -INFINITY;  // max the exponentials are currently relative to (log2 domain), identical in both threads
+    float l_sum = 0.f;         // this thread's share of the row sum
     const float2 sc2 = make_float2(p.scale_log2, p.scale_log2);
     for (int j = 0; j < n_kv; ++j) {
       mbar_wait(&sfull[t], j & 1);
       tc_fence_after();
-      const int valid = p.Lk - j * KT;  // columns >= valid are padding (TMA zero fill); only the last tile is ragged
-      uint32_t pk[64];                  // P as packed bf16x2, stored over S only after the max check below
+      const int valid = p.Lk - j * KT - half * 64;   // my columns >= valid are padding (only the last tile is ragged)
+      uint32_t pk[32];                                // my 64 keys as packed bf16x2, stored only after the max check
       float tile_sum = 0.f, tile_max = -INFINITY;
-      // One pass over S (two 64-column halves straight from TMEM): P = exp2(S*c - m_ref), row sum, raw row max.
       auto exp_pass = [&](const float m_ref) {
         const float2 neg_m2 = make_float2(-m_ref, -m_ref);
         float2 acc0 = make_float2(0.f, 0.f), acc1 = make_float2(0.f, 0.f);
         float mx0 = -INFINITY, mx1 = -INFINITY;
 #pragma unroll
-        for (int c = 0; c < 4; c += 2) {
-          uint32_t r0[32], r1[32];
-          tmem_ld32(s_addr + c * 32, r0);
-          tmem_ld32(s_addr + (c + 1) * 32, r1);
+        for (int c = 0; c < 2; ++c) {
+          uint32_t rr[32];
+          tmem_ld32(s_addr + c * 32, rr);
           tmem_wait_ld();
-          if (valid < KT) {
+          if (valid < 64) {
 #pragma unroll
-            for (int i = 0; i < 32; ++i) {
-              if (c * 32 + i >= valid) r0[i] = 0xff800000u;  // -inf
-              if ((c + 1) * 32 + i >= valid) r1[i] = 0xff800000u;
-            }
+            for (int i = 0; i < 32; ++i)
+              if (c * 32 + i >= valid) rr[i] = 0xff800000u;  // -inf
           }
 #pragma unroll
-          for (int i = 0; i < 32; i += 2) {
-            mx0 = fmax3(mx0, __uint_as_float(r0[i]), __uint_as_float(r0[i + 1]));
-            mx1 = fmax3(mx1, __uint_as_float(r1[i]), __uint_as_float(r1[i + 1]));
-            float2 xa = ffma2(make_float2(__uint_as_float(r0[i]), __uint_as_float(r0[i + 1])), sc2, neg_m2);
-            float2 xb = ffma2(make_float2(__uint_as_float(r1[i]), __uint_as_float(r1[i + 1])), sc2, neg_m2);
+          for (int i = 0; i < 32; i += 4) {
+            mx0 = fmax3(mx0, __uint_as_float(rr[i]), __uint_as_float(rr[i + 1]));
+            mx1 = fmax3(mx1, __uint_as_float(rr[i + 2]), __uint_as_float(rr[i + 3]));
+            float2 xa = ffma2(make_float2(__uint_as_float(rr[i]), __uint_as_float(rr[i + 1])), sc2, neg_m2);
+            float2 xb = ffma2(make_float2(__uint_as_float(rr[i + 2]), __uint_as_float(rr[i + 3])), sc2, neg_m2);
             float2 pa, pb;
-            if (((i >> 1) & 3) == 3) {   // 1 pair in 4 goes to the FMA pipe instead of MUFU (compile-time pattern)
-              pa = exp2_fma2(xa);
-              pb = exp2_fma2(xb);
-            } else {
-              pa = make_float2(fast_exp2(xa.x), fast_exp2(xa.y));
-              pb = make_float2(fast_exp2(xb.x), fast_exp2(xb.y));
-            }
+            pa = make_float2(fast_exp2(xa.x), fast_exp2(xa.y));
+            if ((i & 4) != 0) pb = exp2_fma2(xb);   // 1 pair in 4 on the FMA pipe instead of MUFU (compile-time pattern)
+            else pb = make_float2(fast_exp2(xb.x), fast_exp2(xb.y));
             acc0 = fadd2(acc0, pa);
             acc1 = fadd2(acc1, pb);
-            pk[c * 16 + (i >> 1)] = pack_bf16x2(pa.x, pa.y);        // keys 32c + i, +1       -> packed column 16c + i/2
-            pk[c * 16 + 16 + (i >> 1)] = pack_bf16x2(pb.x, pb.y);   // keys 32(c+1) + i, +1   -> packed column 16(c+1) + i/2
+            pk[c * 16 + (i >> 1)] = pack_bf16x2(pa.x, pa.y);
+            pk[c * 16 + (i >> 1) + 1] = pack_bf16x2(pb.x, pb.y);
           }
         }
         tile_sum = (acc0.x + acc0.y) + (acc1.x + acc1.y);
         tile_max = fmaxf(mx0, mx1);
       };
       if (j == 0) {
-        // first tile: the reference max must be the true row max (one extra read of S from TMEM)
-        float mx0 = -INFINITY, mx1 = -INFINITY;
+        // first tile: the reference max must be the true row max over all 128 keys (one extra read of S from TMEM)
+        float mx = -INFINITY;
 #pragma unroll
-        for (int c = 0; c < 4; c += 2) {
-          uint32_t r0[32], r1[32];
-          tmem_ld32(s_addr + c * 32, r0);
-          tmem_ld32(s_addr + (c + 1) * 32, r1);
+        for (int c = 0; c < 2; ++c) {
+          uint32_t rr[32];
+          tmem_ld32(s_addr + c * 32, rr);
           tmem_wait_ld();
 #pragma unroll
-          for (int i = 0; i < 32; i += 2) {
-            if (c * 32 + i + 1 < valid) mx0 = fmax3(mx0, __uint_as_float(r0[i]), __uint_as_float(r0[i + 1]));
-            else if (c * 32 + i < valid) mx0 = fmaxf(mx0, __uint_as_float(r0[i]));
-            if ((c + 1) * 32 + i + 1 < valid) mx1 = fmax3(mx1, __uint_as_float(r1[i]), __uint_as_float(r1[i + 1]));
-            else if ((c + 1) * 32 + i < valid) mx1 = fmaxf(mx1, __uint_as_float(r1[i]));
-          }
+          for (int i = 0; i < 32; ++i)
+            if (c * 32 + i < valid) mx = fmaxf(mx, __uint_as_float(rr[i]));
         }
-        m_used = fmaxf(mx0, mx1) * p.scale_log2;
+        x_mine[0] = mx;                                      // slot 0 (j & 1 == 0)
+        named_bar_sync(1 + t, 256);
+        m_used = fmaxf(mx, x_peer[0]) * p.scale_log2;
         exp_pass(m_used);
       } else {
-        // optimistic: exponentiate against the stale max while tracking this tile's max; exact unless the max grew
-        // by more than 8 (log2 units), in which case O and l are rescaled and the tile is redone (rare after tile 0)
+        // optimistic: exponentiate against the stale max while tracking this tile's max; exact unless the row max grew
+        // by more than 8 (log2 units): then O and l are rescaled and the tile is redone (rare after the first tiles)
         exp_pass(m_used);
-        const float m_new = fmaxf(m_used, tile_max * p.scale_log2);
-        if (__any_sync(0xffffffffu, m_new > m_used + 8.0f)) {   // warp-uniform: tcgen05.ld/st are warp-collective
+        x_mine[(j & 1) * 512] = tile_max;
+        named_bar_sync(1 + t, 256);
+        const float m_new = fmaxf(m_used, fmaxf(tile_max, x_peer[(j & 1) * 512]) * p.scale_log2);
+        // same rows in the same lanes of the partner warp => both warps take the same (warp-uniform) branch
+        if (__any_sync(0xffffffffu, m_new > m_used + 8.0f)) {
           const float alpha = fast_exp2(m_used - m_new);
           l_sum *= alpha;
           m_used = m_new;
 #pragma unroll 1
-          for (int c = 0; c < 4; ++c) {
+          for (int c = 0; c < 2; ++c) {
             uint32_t o[32];
             tmem_ld32(o_addr + c * 32, o);
             tmem_wait_ld();
@@ -257,31 +262,30 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         }
       }
       l_sum += tile_sum;
-      {
-        uint32_t(&lo)[32] = *reinterpret_cast<uint32_t(*)[32]>(&pk[0]);
-        uint32_t(&hi)[32] = *reinterpret_cast<uint32_t(*)[32]>(&pk[32]);
-        tmem_st32(s_addr, lo);        // packed columns [0,32)  = keys [0,64)
-        tmem_st32(s_addr + 32, hi);   // packed columns [32,64) = keys [64,128)
-      }
+      tmem_st32(s_addr, pk);          // packed columns [64h, 64h + 32) = my keys [64h, 64h + 64)
       tmem_wait_st();
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&pfull[t]);
     }
-    // epilogue: O / l -> bf16 -> global; LSE
+    // epilogue: row sum = both halves' shares; O / l -> bf16 -> global (64 columns per thread); LSE by half 0
+    x_mine[(n_kv & 1) * 512] = l_sum;
+    named_bar_sync(1 + t, 256);
+    const float l_tot = l_sum + x_peer[(n_kv & 1) * 512];
     mbar_wait(ofull, 0);
     tc_fence_after();
-    const float inv_l = 1.0f / l_sum;
+    const float inv_l = 1.0f / l_tot;
     const bool row_ok = row < p.Lq;
     __nv_bfloat16* orow;
     if (p.n_peer > 0) {
-      const int r = row_ok ? row / p.L_loc : 0;
-      orow = p.o_peer[r] + (int64_t)(row - r * p.L_loc) * p.o_ld_tok + (int64_t)(p.head_off + head) * p.o_ld_head;
+      const int rk = row_ok ? row / p.L_loc : 0;
+      orow = p.o_peer[rk] + (int64_t)(row - rk * p.L_loc) * p.o_ld_tok + (int64_t)(p.head_off + head) * p.o_ld_head;
     } else {
       orow = p.o + (int64_t)row * p.o_ld_tok + (int64_t)head * p.o_ld_head;
     }
+    orow += half * 64;
 #pragma unroll 1
-    for (int c = 0; c < 4; ++c) {
+    for (int c = 0; c < 2; ++c) {
       uint32_t o[32];
       tmem_ld32(o_addr + c * 32, o);
       tmem_wait_ld();
@@ -298,12 +302,12 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       }
       __syncwarp();
     }
-    if (row_ok && p.lse) p.lse[(int64_t)head * p.Lq + row] = (m_used + log2f(l_sum)) * 0.6931471805599453f;
+    if (row_ok && half == 0 && p.lse) p.lse[(int64_t)head * p.Lq + row] = (m_used + log2f(l_tot)) * 0.6931471805599453f;
   }
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 9) {
+  if (warp == AW_MMA) {
     tc_fence_after();
     tmem_dealloc<512>(tmem_base);
   }
