@@ -25,9 +25,11 @@ sys.path.insert(0, ROOT)
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--blocks", type=int, default=8)
-    ap.add_argument("--m", type=int, default=2)
+    ap.add_argument("--nograd-forwards", dest="m", type=int, default=2)
     ap.add_argument("--latent", default="21,60,104")
     ap.add_argument("--steps", type=int, default=2)
+    ap.add_argument("--i2v", action="store_true", help="image-to-video architecture (in_dim 36, CLIP tokens, y conditioning)")
+    ap.add_argument("--opt", action="store_true", help="also run the sharded-gradient AdamW step (reduce-scatter, clip, update, all-gather)")
     args = ap.parse_args()
     import torch.distributed as dist
     from prfl_b200 import _lib, parallel
@@ -44,9 +46,10 @@ def main():
     L = fr * (hh // 2) * (ww // 2)
     torch.manual_seed(0)
     with torch.device(dev):
-        vgm = WanModel(model_type="t2v", dim=5120, ffn_dim=13824, num_heads=40, num_layers=args.blocks)
+        mt, ind = ("i2v", 36) if args.i2v else ("t2v", 16)
+        vgm = WanModel(model_type=mt, in_dim=ind, dim=5120, ffn_dim=13824, num_heads=40, num_layers=args.blocks)
         vgm.head.head.weight.data.normal_(0, 0.02)                  # the reference zero-inits it (model.py:729)
-        lrm = WanModel(model_type="t2v", dim=5120, ffn_dim=13824, num_heads=40, num_layers=8)
+        lrm = WanModel(model_type=mt, in_dim=ind, dim=5120, ffn_dim=13824, num_heads=40, num_layers=8)
         lrm.head = None
         qa = QueryAttention(5120, 1, 8, dropout=0.0, return_type="query")
         mlp = MLP(5120)
@@ -54,8 +57,17 @@ def main():
         for p in mod.parameters():
             p.requires_grad_(False)                                 # frozen reward model: dgrad only
     vgm.train()
+    opt = None
+    if args.opt:
+        from prfl_b200.sharding import ShardedAdamW
+        opt = ShardedAdamW(vgm, lr=1e-6, weight_decay=0.0)          # AdamW over transformer params only (train_prfl.py:482-491)
     latent = torch.randn(16, fr, hh, ww, device=dev)
     ctx = [torch.randn(512, 4096, device=dev) * 0.08]
+    extra = {}
+    if args.i2v:
+        mask = torch.zeros(4, fr, hh, ww, device=dev)
+        mask[:, 0] = 1.0                                            # train_prfl.py:537-542
+        extra = dict(clip_fea=torch.randn(1, 257, 1280, device=dev), y=[torch.cat([mask, torch.randn(16, fr, hh, ww, device=dev)])])
     dt = 0.025
 
     def ev():
@@ -69,20 +81,23 @@ def main():
         with torch.no_grad():
             for i in range(args.m):
                 t = torch.tensor([999.0 - 25 * i], device=dev)
-                pred = vgm(x=[lat], t=t, context=ctx, seq_len=L)[0]
+                pred = vgm(x=[lat], t=t, context=ctx, seq_len=L, **extra)[0]
                 lat = lat - dt * pred
         marks["nograd_done"] = ev()
         t = torch.tensor([999.0 - 25 * args.m], device=dev)
-        pred = vgm(x=[lat], t=t, context=ctx, seq_len=L)[0]
+        pred = vgm(x=[lat], t=t, context=ctx, seq_len=L, **extra)[0]
         marks["grad_fwd_done"] = ev()
         lat2 = lat - dt * pred
-        feats = torch.stack(lrm(x=[lat2], t=t - 25, context=ctx, seq_len=L, output_features=True, selected_layers=[8]))
+        feats = torch.stack(lrm(x=[lat2], t=t - 25, context=ctx, seq_len=L, output_features=True, selected_layers=[8], **extra))
         reward = mlp(qa(feats))
         loss = 0.1 * torch.relu(2.0 - reward).mean()
         marks["lrm_fwd_done"] = ev()
         loss.backward()
         marks["bwd_done"] = ev()
-        return marks, float(loss)
+        if opt is not None:
+            opt.step(max_norm=1.0)                                  # clip_grad_norm_(1.0) + optimizer.step (train_prfl.py:825-830)
+            marks["opt_done"] = ev()
+        return marks, float(loss.detach())
 
     one_step()                                                      # warm-up (operand caches, allocator)
     vgm.zero_grad(set_to_none=True)
@@ -98,12 +113,12 @@ def main():
     avg = {k: sum(r[k] for r in rows) / len(rows) for k in rows[0]}
     # algorithmic FLOPs per block at this L (SURVEY.md Appendix A formulae)
     lin = 597.7e6 * L + 4 * 5120 * 5120 * 512
-    att = 4.0 * L * L * 128 * 40 + 4.0 * L * 512 * 128 * 40
+    att = 4.0 * L * L * 128 * 40 + 4.0 * L * (512 + (257 if args.i2v else 0)) * 128 * 40
     fwd_blk = (lin + att) / world
     bwd_blk = (2 * lin + 2.5 * att) / world
     nb = args.blocks
     out = {
-        "workload": f"PRFL refl-shaped step, VGM {nb} blocks (14B dims) + frozen 8-block reward model, L={L}, m={args.m}, SP={world}",
+        "workload": f"PRFL refl-shaped step ({'i2v' if args.i2v else 't2v'}), VGM {nb} blocks (14B dims) + frozen 8-block reward model, L={L}, m={args.m}, SP={world}",
         "ms": avg, "loss": loss, "gpu_launches_per_step": _lib.launch_count() / args.steps,
         "nograd_fwd_tflops": args.m * nb * fwd_blk / (avg["nograd_done"] * 1e-3) / 1e12 if args.m else None,
         "grad_fwd_tflops": nb * fwd_blk / (avg["grad_fwd_done"] * 1e-3) / 1e12,
@@ -111,6 +126,7 @@ def main():
         # backward = recompute fwd + bwd of the VGM blocks, and recompute + dgrad (here: full bwd kernels) of 8 LRM blocks
         "bwd_tflops_algorithmic": ((nb + 8) * (fwd_blk + bwd_blk)) / (avg["bwd_done"] * 1e-3) / 1e12,
         "step_ms": sum(avg.values()),
+        "step_tokens_per_s": L * (args.m + 2) / (sum(avg.values()) * 1e-3),   # DiT forwards per step: m no-grad + 1 grad + 1 reward
         "peak_mem_gb": torch.cuda.max_memory_allocated() / 1e9,
     }
     if int(os.environ.get("RANK", "0")) == 0:
