@@ -53,6 +53,23 @@ def case_model(M, name, cfg, latent, seed_w, seed_in, selected, with_grad=True):
     print(name, "out", [tuple(o.shape) for o in out], "feat", [tuple(f.shape) for f in feats])
 
 
+def case_ragged(M, name, cfg, latents, seq_len, seed_w, seed_in):
+    """Two samples of different sizes in one call, zero-padded to seq_len (model.py:578-587; k_lens masking :188-193)."""
+    sd = synth.make_wan_state_dict(cfg, seed_w)
+    g = torch.Generator().manual_seed(seed_in)
+    x = [torch.randn(16, *lat, generator=g) for lat in latents]
+    ctx = [torch.randn(n, cfg.text_dim, generator=g) * 0.08 for n in (40, 17)]
+    t = torch.tensor([400.0, 725.0])
+    m = ref_model(M, cfg, sd)
+    with torch.no_grad():
+        out = m(x=x, t=t, context=ctx, seq_len=seq_len)
+        feats = m(x=x, t=t, context=ctx, seq_len=seq_len, output_features=True, selected_layers=[2])
+    fx = dict(cfg=cfg.kwargs(), latents=latents, seq_len=seq_len, seed_w=seed_w, seed_in=seed_in,
+              out=[o.clone() for o in out], features=[f.clone() for f in feats])
+    torch.save(fx, os.path.join(HERE, name + ".pt"))
+    print(name, "out", [tuple(o.shape) for o in out], "feat", [tuple(f.shape) for f in feats])
+
+
 def case_reward(M, N, name, cfg, latent, nblocks, seed_w, seed_in, slice_only=False):
     sd = synth.make_wan_state_dict(cfg, seed_w)
     inp = synth.make_inputs(cfg, latent, seed_in)
@@ -165,3 +182,4 @@ if __name__ == "__main__":
     # BASELINE.json configs[0]: 1.3B architecture, 8 blocks, 17f x 240 x 416 -> latent 5 x 30 x 52
     case_reward(M, N, "cfg0_reward", synth.cfg_1_3b(layers=8), (5, 30, 52), 8, 40, 41, slice_only=True)
     case_a2a("a2a_gloo2")
+    case_ragged(M, "tiny_t2v_ragged", synth.tiny_cfg("t2v"), [(5, 12, 20), (3, 10, 14)], 320, 60, 61)

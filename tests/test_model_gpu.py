@@ -83,3 +83,26 @@ def test_reward_logit(name, tol):
 def test_smoke_entry():
     import __graft_entry__ as g
     g.smoke()
+
+
+def test_ragged_batch_vs_reference_golden():
+    """B = 2 samples of different sizes (300 and 105 tokens) zero-padded to seq_len = 320: per-sample grids, RoPE tables,
+    key masking to each sample's length and per-sample timesteps, against the real reference's output."""
+    fx = golden("tiny_t2v_ragged")
+    cfg = O.WanConfig(**fx["cfg"])
+    sd = synth.make_wan_state_dict(cfg, fx["seed_w"])
+    g = torch.Generator().manual_seed(fx["seed_in"])
+    x = [torch.randn(16, *lat, generator=g) for lat in fx["latents"]]
+    ctx = [torch.randn(n, cfg.text_dim, generator=g) * 0.08 for n in (40, 17)]
+    t = torch.tensor([400.0, 725.0])
+    m = _model(cfg, sd)
+    with torch.no_grad():
+        out = m(x=[u.cuda() for u in x], t=t.cuda(), context=[c.cuda() for c in ctx], seq_len=fx["seq_len"])
+        feats = m(x=[u.cuda() for u in x], t=t.cuda(), context=[c.cuda() for c in ctx], seq_len=fx["seq_len"],
+                  output_features=True, selected_layers=[2])
+    for i, (o, r) in enumerate(zip(out, fx["out"])):
+        assert o.shape == r.shape
+        _check(o, r, f"sample {i}")
+    # features include the padded rows (the reference computes them too); compare the valid rows of each sample
+    for i, n in enumerate((300, 105)):
+        _check(feats[0][i, :n], fx["features"][0][i, :n], f"features sample {i}")

@@ -31,7 +31,7 @@ def _worker(rank, world, port, q):
     (gathered * torch.arange(gathered.shape[1]).view(1, -1, 1, 1)).sum().backward()
     t = torch.full((3,), float(rank))
     P.broadcast(t)
-    q.put((rank, out.detach(), back.detach(), mine.grad.clone(), gathered.detach(), x.grad.clone(), t))
+    q.put((rank,) + tuple(v.detach().numpy().copy() for v in (out, back, mine.grad, gathered, x.grad, t)))   # numpy: no fd passing
     dist.barrier()
     dist.destroy_process_group()
 
@@ -46,7 +46,7 @@ def test_ulysses_gloo_world2_matches_reference():
     res = sorted([q.get(timeout=180) for _ in range(world)], key=lambda r: r[0])
     [p.join(60) for p in procs]
     for r in range(world):
-        _, out, back, grad, gathered, xg, t = res[r]
+        _, out, back, grad, gathered, xg, t = (res[r][0],) + tuple(torch.from_numpy(v) for v in res[r][1:])
         assert torch.equal(out, fx["out"][r])            # forward exchange == reference's
         assert torch.equal(back, fx["back"][r])          # round trip
         assert torch.equal(grad, fx["grad"][r])          # backward = swapped exchange (communication.py:143-152)

@@ -28,7 +28,7 @@ def _data(rank):
     return torch.randn(11, 7, generator=g), torch.randn(11, 3, generator=g)
 
 
-def _worker(rank, world, port, q):
+def _worker(rank, world, port, q, hooks=False):
     sys.path.insert(0, ROOT)
     import torch.distributed as dist
     os.environ.update(RANK=str(rank), WORLD_SIZE=str(world), MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
@@ -37,22 +37,28 @@ def _worker(rank, world, port, q):
     m = Toy()
     assert len(fsdp_units(m)) == 4
     opt = ShardedAdamW(m, lr=1e-2, weight_decay=0.01)
+    if hooks:
+        opt.attach_hooks()          # streaming mode: each unit is reduce-scattered and freed inside backward
     norms = []
     for _ in range(3):
         x, y = _data(rank)
         ((m(x) - y) ** 2).mean().backward()
         norms.append(float(opt.step(max_norm=1.0)))
         assert all(p.grad is None for p in m.parameters())
-    q.put((rank, [p.detach().clone() for p in m.parameters()], norms))
+    q.put((rank, [p.detach().numpy().copy() for p in m.parameters()], norms))    # numpy: no fd passing through the queue
     dist.barrier()
     dist.destroy_process_group()
 
 
-def test_sharded_adamw_matches_dense_adamw():
+import pytest
+
+
+@pytest.mark.parametrize("hooks", [False, True])
+def test_sharded_adamw_matches_dense_adamw(hooks):
     world = 2
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    procs = [ctx.Process(target=_worker, args=(r, world, 29647, q)) for r in range(world)]
+    procs = [ctx.Process(target=_worker, args=(r, world, 29647 + int(hooks), q, hooks)) for r in range(world)]
     [p.start() for p in procs]
     res = sorted([q.get(timeout=180) for _ in range(world)], key=lambda r: r[0])
     [p.join(60) for p in procs]
@@ -69,5 +75,5 @@ def test_sharded_adamw_matches_dense_adamw():
         opt.step()
     for r in range(world):
         for a, b in zip(res[r][1], m.parameters()):
-            torch.testing.assert_close(a, b.detach(), rtol=1e-5, atol=1e-6)
+            torch.testing.assert_close(torch.from_numpy(a), b.detach(), rtol=1e-5, atol=1e-6)
         torch.testing.assert_close(torch.tensor(res[r][2]), torch.tensor(ref_norms), rtol=1e-5, atol=1e-6)

@@ -60,7 +60,8 @@ def main():
     opt = None
     if args.opt:
         from prfl_b200.sharding import ShardedAdamW
-        opt = ShardedAdamW(vgm, lr=1e-6, weight_decay=0.0)          # AdamW over transformer params only (train_prfl.py:482-491)
+        # AdamW over transformer params only (train_prfl.py:482-491); gradients are reduce-scattered block by block inside backward
+        opt = ShardedAdamW(vgm, lr=1e-6, weight_decay=0.0).attach_hooks()
     latent = torch.randn(16, fr, hh, ww, device=dev)
     ctx = [torch.randn(512, 4096, device=dev) * 0.08]
     extra = {}
