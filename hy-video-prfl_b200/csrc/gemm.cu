@@ -13,7 +13,7 @@ namespace prfl {
 constexpr int BM = 128, BN = 256, BK = 64;
 constexpr int A_STAGE = BM * BK * 2;  // 16 KB
 constexpr int GEMM_THREADS = 192;
-constexpr int GROUP_M = 8;
+
 // CG = 1: one CTA per 128 x 256 tile, B stage 32 KB, 4 stages.
 // CG = 2: a CTA pair (cluster of 2, tcgen05 cta_group::2) per 256 x 256 tile: each CTA stages its 128 rows of A and HALF
 //         of B (128 of the 256 columns), the leader issues UMMA 256x256x16 that reads both CTAs' shared memory and writes
@@ -35,13 +35,14 @@ struct GemmParams {
   int64_t ldaux;
   int M, N, K, epi, beta;
   int tiles_m, tiles_n, num_kb;
+  int group_m;   // raster: tiles are walked m-fastest inside groups of `group_m` row-tiles so a wave shares A and B panels in L2
 };
 
-__device__ __forceinline__ void tile_coords(int tile, int tiles_m, int tiles_n, int& m_blk, int& n_blk) {
-  const int group = GROUP_M * tiles_n;
+__device__ __forceinline__ void tile_coords(int tile, int tiles_m, int tiles_n, int group_m, int& m_blk, int& n_blk) {
+  const int group = group_m * tiles_n;
   const int g = tile / group;
-  const int first_m = g * GROUP_M;
-  const int gm = min(tiles_m - first_m, GROUP_M);
+  const int first_m = g * group_m;
+  const int gm = min(tiles_m - first_m, group_m);
   const int r = tile - g * group;
   m_blk = first_m + r % gm;
   n_blk = r / gm;
@@ -100,7 +101,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       };
       for (int tile = unit; tile < total_tiles; tile += n_units) {
         int m_blk, n_blk;
-        tile_coords(tile, p.tiles_m, p.tiles_n, m_blk, n_blk);
+        tile_coords(tile, p.tiles_m, p.tiles_n, p.group_m, m_blk, n_blk);
         const int m0 = (m_blk * CG + cta_rank) * BM, n0 = n_blk * BN + cta_rank * B_ROWS;
         for (int kb = 0; kb < p.num_kb; ++kb, ++it) {
           const int s = it % STAGES;
@@ -164,7 +165,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     uint32_t t = 0;
     for (int tile = unit; tile < total_tiles; tile += n_units, ++t) {
       int m_blk, n_blk;
-      tile_coords(tile, p.tiles_m, p.tiles_n, m_blk, n_blk);
+      tile_coords(tile, p.tiles_m, p.tiles_n, p.group_m, m_blk, n_blk);
       const uint32_t buf = t & 1, aph = (t >> 1) & 1;
       const int row = (m_blk * CG + cta_rank) * BM + quad * 32 + lane;
       const bool row_ok = row < p.M;
@@ -378,6 +379,11 @@ extern "C" int prfl_gemm_bf16(const void* A, int64_t lda, int a_trans, const voi
   p.out = out; p.ldc = ldc; p.bias = bias; p.gate = gate; p.aux = (__nv_bfloat16*)aux_bf16; p.ldaux = ldaux;
   p.M = M; p.N = N; p.K = K; p.epi = epi; p.beta = beta;
   p.tiles_m = (M + BM * cg - 1) / (BM * cg); p.tiles_n = (N + BN - 1) / BN; p.num_kb = (K + BK - 1) / BK;
+  static int group_env = [] {
+    const char* e = getenv("PRFL_GEMM_GROUP_M");
+    return e ? atoi(e) : 0;
+  }();
+  p.group_m = group_env > 0 ? group_env : 8;
   cudaStream_t st = (cudaStream_t)stream;
   if (cg == 2) {
     if (!a_trans && !b_trans) return launch_gemm<false, false, 2>(tmA, tmB, p, st);

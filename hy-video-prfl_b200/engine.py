@@ -168,7 +168,7 @@ def _wgrad(dy: torch.Tensor, x: torch.Tensor) -> torch.Tensor:
     return ops.gemm(dy, x, a_trans=True, b_trans=True, epi=ops.EPI_F32)
 
 
-def block_backward(blk, st: Dict, dx: torch.Tensor, need_ctx_grad: bool, need_w: bool = True):
+def block_backward(blk, st: Dict, dx: torch.Tensor, need_ctx_grad: bool, need_w: bool = True, need_e: bool = True):
     """dx: [M, C] fp32 gradient w.r.t. the block output; overwritten with the gradient w.r.t. the block input.
     Returns (grads: name -> fp32 tensor, dem [6, C], dctx [Lc, C] fp32 or None)."""
     sa, ca = blk.self_attn, blk.cross_attn
@@ -183,7 +183,10 @@ def block_backward(blk, st: Dict, dx: torch.Tensor, need_ctx_grad: bool, need_w:
     # ---- FFN ----
     w1, b1 = blk.ffn[0].operands()
     w2, b2 = blk.ffn[2].operands()
-    y2 = ops.gemm(st["f"], w2, bias=b2, epi=ops.EPI_BF16)
+    # the gate / shift / scale gradients feed `modulation` and the time embedding: skipped for frozen blocks whose
+    # conditioning needs no gradient (the reward model in PRFL) — that also saves re-running ffn.2 for the gate gradient
+    need_mod = need_w or need_e
+    y2 = ops.gemm(st["f"], w2, bias=b2, epi=ops.EPI_BF16) if need_mod else None
     dy2, de5 = ops.gate_bwd(dx, y2, em[5])
     del y2
     du = ops.gemm(dy2, w2, b_trans=True, epi=ops.EPI_BF16_DGELU, aux=st["u"])                # [M, ffn]
@@ -194,7 +197,7 @@ def block_backward(blk, st: Dict, dx: torch.Tensor, need_ctx_grad: bool, need_w:
     g["ffn.0.weight"] = wgrad(du, st["h2"])
     g["ffn.0.bias"] = colsum(du)
     del du
-    dsh2, dsc2 = ops.ln_mod_bwd(st["x2"], dh2, em[4], None, st["mean2"], st["rstd2"], dx, True)
+    dsh2, dsc2 = ops.ln_mod_bwd(st["x2"], dh2, em[4], None, st["mean2"], st["rstd2"], dx, need_mod)
     del dh2
 
     # ---- cross-attention ----
@@ -242,7 +245,7 @@ def block_backward(blk, st: Dict, dx: torch.Tensor, need_ctx_grad: bool, need_w:
     del dh3
 
     # ---- self-attention ----
-    dy1, de2 = ops.gate_bwd(dx, st["y1"], em[2])
+    dy1, de2 = ops.gate_bwd(dx, st["y1"] if need_mod else None, em[2])
     wo, _ = sa.o.operands()
     da1 = ops.gemm(dy1, wo, b_trans=True, epi=ops.EPI_BF16)
     g["self_attn.o.weight"] = wgrad(dy1, st["a1"])
@@ -280,8 +283,8 @@ def block_backward(blk, st: Dict, dx: torch.Tensor, need_ctx_grad: bool, need_w:
             g[f"self_attn.{nm}.weight"] = dwqkv[j * C:(j + 1) * C]
             g[f"self_attn.{nm}.bias"] = dbqkv[j * C:(j + 1) * C]
     del dqkv
-    dsh1, dsc1 = ops.ln_mod_bwd(st["x_in"], dh1, em[1], None, st["mean1"], st["rstd1"], dx, True)
-    dem = torch.stack([dsh1, dsc1, de2, dsh2, dsc2, de5])                                     # [6, C]
+    dsh1, dsc1 = ops.ln_mod_bwd(st["x_in"], dh1, em[1], None, st["mean1"], st["rstd1"], dx, need_mod)
+    dem = torch.stack([dsh1, dsc1, de2, dsh2, dsc2, de5]) if need_mod else None              # [6, C]
     dctx = None
     if need_ctx_grad:
         dctx = dctx_parts[0] if len(dctx_parts) == 1 else torch.cat(dctx_parts, dim=0)
@@ -321,21 +324,24 @@ class BlockFn(torch.autograd.Function):
         cb = cb if cb.dtype == torch.bfloat16 else cb.to(torch.bfloat16)
         need_ctx = ctx.needs_input_grad[2]
         need_w = any(ctx.needs_input_grad[8:])
+        need_e = ctx.needs_input_grad[1]
         tot: Dict[str, torch.Tensor] = {}
         dems, dctxs = [], []
         for i in range(B):
             st: Dict = {}
             block_forward(blk, x[i].detach().clone(), em[i], cb[i].contiguous(), int(ctx.seq_lens[i]), ctx.grids[i], ctx.first, st)
-            gi, dem, dctx = block_backward(blk, st, dx[i], need_ctx, need_w)
+            gi, dem, dctx = block_backward(blk, st, dx[i], need_ctx, need_w, need_e)
             del st
             for k, v in gi.items():
                 if v is not None:
                     tot[k] = v if k not in tot else tot[k] + v
             dems.append(dem)
             dctxs.append(dctx)
-        de = torch.stack(dems)                                                                # [B, 6, C]
+        de = torch.stack(dems) if dems[0] is not None else None                               # [B, 6, C]
         if need_w:
             tot["modulation"] = de.sum(0, keepdim=True)
+        if not need_e:
+            de = None
         dctx = torch.stack(dctxs).to(context.dtype) if need_ctx else None
         pg = []
         for nm, p in zip(ctx.names, ctx.blk.parameters()):

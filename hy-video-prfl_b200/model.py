@@ -31,7 +31,7 @@ from .parallel import get_sequence_parallel_state, nccl_info, ulysses_gather_tok
 from .rope import rope_tables
 
 __all__ = ["WanModel", "WanAttentionBlock", "WanSelfAttention", "WanT2VCrossAttention", "WanI2VCrossAttention",
-           "WanRMSNorm", "WanLayerNorm", "Head", "MLPProj", "sinusoidal_embedding_1d", "rope_params"]
+           "WanRMSNorm", "WanLayerNorm", "Head", "MLPProj", "sinusoidal_embedding_1d", "rope_params", "rope_apply"]
 
 T5_CONTEXT_TOKEN_NUMBER = 512
 
@@ -104,6 +104,27 @@ def rope_params(max_seq_len, dim, theta=10000):
     freqs = torch.outer(torch.arange(max_seq_len),
                         1.0 / torch.pow(theta, torch.arange(0, dim, 2).to(torch.float64).div(dim)))
     return torch.polar(torch.ones_like(freqs), freqs)
+
+
+def rope_apply(x, grid_sizes, freqs=None):
+    """API-compatibility helper with the reference's signature (model.py:60-103): x [B, s, n, d] -> fp32, pairs
+    (2j, 2j+1) of every head rotated by the (frame, row, column) angle of the token, tokens past the grid passed through,
+    Ulysses rank offset applied under sequence parallelism.  The model itself never calls this: RoPE is fused into
+    prfl_rmsnorm_rope_fwd; this exists for callers that use the free function.  `freqs` is ignored (tables come from
+    rope.rope_tables, float64-derived)."""
+    b, s, n, d = x.shape
+    sp = get_sequence_parallel_state()
+    P = nccl_info.sp_size if sp else 1
+    rank = nccl_info.rank_within_group if sp else 0
+    out = []
+    for i, g in enumerate(_grid_list(grid_sizes)):
+        cos, sin = rope_tables(g, x.device, d, pad_to=s * P)
+        nrot = s if sp else min(g[0] * g[1] * g[2], s)
+        c, sn = cos[rank * s:rank * s + nrot, None, :], sin[rank * s:rank * s + nrot, None, :]
+        xi = x[i, :nrot].float().reshape(nrot, n, d // 2, 2)
+        y = torch.stack([xi[..., 0] * c - xi[..., 1] * sn, xi[..., 0] * sn + xi[..., 1] * c], dim=-1).reshape(nrot, n, d)
+        out.append(torch.cat([y, x[i, nrot:].float()]))
+    return torch.stack(out)
 
 
 class WanRMSNorm(nn.Module):

@@ -55,3 +55,13 @@ def test_state_dict_keys_match_reference_layout():
     qa, mlp = synth.make_reward_state_dicts(256)
     QueryAttention(256, 1, 8, dropout=0.0, return_type="query").load_state_dict(qa, strict=True)
     MLP(256).load_state_dict(mlp, strict=True)
+
+
+def test_rope_apply_free_function_matches_reference_golden():
+    """`rope_apply(x, grid_sizes, freqs)` keeps the reference signature (model.py:61); torch ops, so it runs on CPU."""
+    from conftest import golden
+    from prfl_b200.model import rope_apply
+    fx = golden("ops")
+    out = rope_apply(fx["rope_in"], torch.tensor([fx["rope_grid"]]), None)
+    assert out.dtype == torch.float32
+    torch.testing.assert_close(out, fx["rope_out"], rtol=1e-5, atol=1e-5)

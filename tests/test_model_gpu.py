@@ -106,3 +106,29 @@ def test_ragged_batch_vs_reference_golden():
     # features include the padded rows (the reference computes them too); compare the valid rows of each sample
     for i, n in enumerate((300, 105)):
         _check(feats[0][i, :n], fx["features"][0][i, :n], f"features sample {i}")
+
+
+def test_flash_attention_free_function_fwd_bwd():
+    """`flash_attention` keeps the reference's signature (attention.py:24-38): fp32 in -> fp32 out, k_lens masking,
+    differentiable; checked against the oracle's restatement."""
+    from prfl_b200.attention import flash_attention
+    g = torch.Generator().manual_seed(5)
+    q = torch.randn(2, 150, 2, 128, generator=g)
+    k = torch.randn(2, 200, 2, 128, generator=g)
+    v = torch.randn(2, 200, 2, 128, generator=g)
+    k_lens = torch.tensor([200, 131])
+    qr, kr, vr = (t.clone().requires_grad_(True) for t in (q, k, v))
+    prec = O._Prec(None)
+    ref = torch.cat([O.flash_attention(qr[i:i + 1], kr[i:i + 1], vr[i:i + 1], prec, int(k_lens[i])) for i in range(2)])
+    cot = torch.randn(ref.shape, generator=g)
+    ref.backward(cot)
+    qc, kc, vc = (t.cuda().requires_grad_(True) for t in (q, k, v))
+    out = flash_attention(qc, kc, vc, k_lens=k_lens)
+    assert out.dtype == torch.float32 and out.shape == ref.shape
+    _check(out, ref.detach(), "flash_attention")
+    out.backward(cot.cuda())
+    for name, a, b in (("dq", qc.grad, qr.grad), ("dk", kc.grad, kr.grad), ("dv", vc.grad, vr.grad)):
+        _check(a, b, name)
+    assert float(kc.grad[1, 131:].abs().max()) == 0.0          # keys beyond k_lens get no gradient
+    with pytest.raises(NotImplementedError):
+        flash_attention(qc, kc, vc, causal=True)
