@@ -38,6 +38,7 @@ _SIGS = {
     "prfl_rmsnorm_rope_bwd": (C.c_int, [_p, _i64, _p, _p, _p, _p, _i64, _p, _p, _i64, _p, _i64, _i64, _i32, _i64, _i64, _p]),
     "prfl_colsum_bf16": (C.c_int, [_p, _i64, _p, _i64, _i32, _p]),
     "prfl_gate_bwd": (C.c_int, [_p, _p, _p, _p, _p, _i64, _i32, _p]),
+    "prfl_attn_bwd_ws_floats": (_i64, [_i32, _i32]),
     "prfl_attn_bwd": (C.c_int, [_p, _i64, _i64] * 5 + [_p, _p] + [_p, _i64, _i64] * 3 + [_i32, _i32, _i32, _f32, _p]),
     "prfl_attn_fwd_p2p": (C.c_int, [_p, _i64, _i64, _p, _i64, _i64, _p, _i64, _i64, _p, _i32, _i32, _i32, _i64, _i64, _p, _i32, _i32,
                                     _i32, _f32, _p]),

@@ -129,6 +129,17 @@ __device__ __forceinline__ float2 fadd2(float2 a, float2 b) {
   return d;
 }
 
+__device__ __forceinline__ float2 fmul2(float2 a, float2 b) {
+  float2 d;
+  asm("{\n\t.reg .b64 ra, rb, rd;\n\t"
+      "mov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\t"
+      "mul.rn.f32x2 rd, ra, rb;\n\t"
+      "mov.b64 {%0, %1}, rd;\n\t}"
+      : "=f"(d.x), "=f"(d.y)
+      : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
+  return d;
+}
+
 // exp2 on the FMA pipe (for a fraction of the softmax elements, the MUFU pipe being the co-bottleneck of attention):
 // round-to-nearest split x = n + r with the 1.5*2^23 magic constant, degree-3 minimax 2^r on [-0.5, 0.5]
 // (max rel. error 7.5e-5, far below bf16's 3.9e-3), exponent added with one integer op.  x is clamped at -120.

@@ -178,7 +178,7 @@ def attn_bwd(q, k, v, o, dout, lse, dq=None, dk=None, dv=None, scale: Optional[f
     dq = torch.empty(Lq, H, 128, dtype=bf16, device=q.device) if dq is None else dq
     dk = torch.empty(Lk, H, 128, dtype=bf16, device=q.device) if dk is None else dk
     dv = torch.empty(Lk, H, 128, dtype=bf16, device=q.device) if dv is None else dv
-    delta = torch.empty(H, Lq, dtype=f32, device=q.device)
+    ws = torch.empty(int(lib().prfl_attn_bwd_ws_floats(Lq, H)), dtype=f32, device=q.device)
     _req(lse, f32, "attn_bwd.lse")
     assert lse.shape == (H, Lq) and lse.is_contiguous()
     if scale is None:
@@ -186,7 +186,7 @@ def attn_bwd(q, k, v, o, dout, lse, dq=None, dk=None, dv=None, scale: Optional[f
     args = []
     for t in (q, k, v, o, dout):
         args += [_p(t), t.stride(0), t.stride(1)]
-    args += [_p(lse), _p(delta)]
+    args += [_p(lse), _p(ws)]
     for t in (dq, dk, dv):
         assert t.dtype == bf16 and t.stride(2) == 1
         args += [_p(t), t.stride(0), t.stride(1)]

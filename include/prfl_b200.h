@@ -141,12 +141,15 @@ int prfl_attn_fwd_p2p(const void* q, int64_t q_ld_tok, int64_t q_ld_head, const 
                       int n_peer, int L_loc, int head_off, int64_t o_ld_tok, int64_t o_ld_head, float* lse, int Lq, int Lk,
                       int H, float scale, prfl_stream_t stream);
 /* Backward (replaces flash_attn's bwd kernels reached through autograd from the same call sites): dq, dk, dv (bf16,
- * same addressing as q/k/v) from q, k, v, o, dout and the forward's lse.  delta: [H, Lq] f32 workspace, filled here
- * with rowsum(dout * o).  Two tcgen05 kernels (dK/dV with keys resident, dQ with queries resident); no atomics. */
+ * same addressing as q/k/v) from q, k, v, o, dout and the forward's lse.  ws: f32 workspace of
+ * prfl_attn_bwd_ws_floats(Lq, H) elements (16-byte aligned), filled here with -lse*log2(e) and -rowsum(dout * o) padded
+ * to whole 64-query blocks.  Two tcgen05 kernels (dK/dV with keys resident, dQ with queries resident, the resident
+ * operands held in tensor memory); no atomics, deterministic. */
+int64_t prfl_attn_bwd_ws_floats(int Lq, int H);
 int prfl_attn_bwd(const void* q, int64_t q_ld_tok, int64_t q_ld_head, const void* k, int64_t k_ld_tok,
                   int64_t k_ld_head, const void* v, int64_t v_ld_tok, int64_t v_ld_head, const void* o,
                   int64_t o_ld_tok, int64_t o_ld_head, const void* dout, int64_t do_ld_tok, int64_t do_ld_head,
-                  const float* lse, float* delta, void* dq, int64_t dq_ld_tok, int64_t dq_ld_head, void* dk,
+                  const float* lse, float* ws, void* dq, int64_t dq_ld_tok, int64_t dq_ld_head, void* dk,
                   int64_t dk_ld_tok, int64_t dk_ld_head, void* dv, int64_t dv_ld_tok, int64_t dv_ld_head, int Lq, int Lk,
                   int H, float scale, prfl_stream_t stream);
 
