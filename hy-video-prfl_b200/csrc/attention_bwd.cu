@@ -430,8 +430,10 @@ extern "C" int prfl_attn_bwd(const void* q, int64_t q_ld_tok, int64_t q_ld_head,
   TM(tKs, k, Lk, k_ld_tok, k_ld_head, SUB)
   TM(tVs, v, Lk, v_ld_tok, v_ld_head, SUB)
 #undef TM
-  // PRFL_ATTN_BWD_DKDV=ss selects the shared-memory-resident dK/dV kernel (64-query units) for A/B measurements
-  static const bool dkdv_ts = [] { const char* e = getenv("PRFL_ATTN_BWD_DKDV"); return !(e && e[0] == 's'); }();
+  // dK/dV default: keys resident in shared memory, 64-query units (31.4 ms at L = 32 760 x 40 heads).  The all-TS form has
+  // to shrink its units to 32 queries to fit K, V in tensor memory next to two accumulators; that halves the latency
+  // budget of the softmax-gradient stage (512 tensor cycles) and measures slower (33.5 ms): PRFL_ATTN_BWD_DKDV=ts for A/B.
+  static const bool dkdv_ts = [] { const char* e = getenv("PRFL_ATTN_BWD_DKDV"); return e && e[0] == 't'; }();
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(attn_bwd_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, BwdSmem<true>::BYTES);

@@ -370,3 +370,46 @@ def a2a_pack(strided: torch.Tensor, packed: torch.Tensor, P: int, unpack: bool =
     check(lib().prfl_a2a_pack(_p(strided), strided.stride(0), strided.stride(1), _p(packed), L_loc, H, P, int(unpack), _stream()),
           "prfl_a2a_pack")
     return strided if unpack else packed
+
+
+# ------------------------------------------------------------------------------------------------
+# PRFL chain glue (scheduler step)
+# ------------------------------------------------------------------------------------------------
+def unipc_step(sample, model_output, last_sample, hist, sigma: float, corr_coef, pred_coef):
+    """One fused FlowUniPC update (fm_solvers_unipc.py:655-739).  All tensors fp32, same shape, contiguous.
+    hist: previous x0 predictions, newest first (up to 3).  corr_coef: 5 floats or None; pred_coef: 5 floats.
+    Returns (x0, corrected | None, prev)."""
+    import ctypes as C
+    for t, n in ((sample, "sample"), (model_output, "model_output")):
+        _req(t, f32, "unipc_step." + n)
+        assert t.is_contiguous() and t.shape == sample.shape
+    hs = [None, None, None]
+    for i, h in enumerate(hist[:3]):
+        if h is not None:
+            _req(h, f32, "unipc_step.hist")
+            assert h.is_contiguous() and h.shape == sample.shape
+            hs[i] = h
+    x0 = torch.empty_like(sample)
+    prev = torch.empty_like(sample)
+    corrected = None
+    cc = None
+    if corr_coef is not None:
+        _req(last_sample, f32, "unipc_step.last_sample")
+        assert last_sample.is_contiguous() and last_sample.shape == sample.shape
+        corrected = torch.empty_like(sample)
+        cc = (C.c_float * 5)(*[float(c) for c in corr_coef])
+    pc = (C.c_float * 5)(*[float(c) for c in pred_coef])
+    check(lib().prfl_unipc_step(_p(sample), _p(model_output), _p(last_sample) if cc is not None else None, _p(hs[0]), _p(hs[1]),
+                                _p(hs[2]), float(sigma), cc, pc, _p(x0), _p(corrected), _p(prev), sample.numel(), _stream()),
+          "prfl_unipc_step")
+    return x0, corrected, prev
+
+
+def scale2(g, a: float, b: Optional[float] = None):
+    """(a * g, b * g) in one pass (b optional) — backward of unipc_step."""
+    _req(g, f32, "scale2.g")
+    g = g.contiguous()
+    ya = torch.empty_like(g)
+    yb = torch.empty_like(g) if b is not None else None
+    check(lib().prfl_scale2_f32(_p(g), float(a), _p(ya), float(b or 0.0), _p(yb), g.numel(), _stream()), "prfl_scale2_f32")
+    return ya, yb

@@ -79,3 +79,60 @@ def load():
         M.flash_attention = sdpa_flash
         torch.cuda.synchronize = lambda *a, **k: None
     return M, N
+
+
+def load_scheduler():
+    """Import the UNMODIFIED reference `FlowUniPCMultistepScheduler` (diffusers_lite/wan/utils/fm_solvers_unipc.py).
+    `diffusers` is not installed here, so the three things the file takes from it are stubbed with the behaviour the
+    scheduler relies on: `register_to_config` records the constructor arguments (defaults included) in `self.config`,
+    `SchedulerOutput` carries `prev_sample`, `deprecate` is a no-op.  The arithmetic is entirely the reference's."""
+    import importlib.util
+    import inspect
+
+    name = "_prfl_ref_fm_solvers_unipc"
+    if name in sys.modules:
+        return sys.modules[name]
+    load()                                               # registers the base `diffusers` stubs
+    cu = sys.modules["diffusers.configuration_utils"]
+
+    class _Cfg(dict):
+        __getattr__ = dict.__getitem__
+
+    class ConfigMixin:
+        def register_to_config(self, **kw):
+            if not hasattr(self, "config"):
+                self.config = _Cfg()
+            self.config.update(kw)
+
+    def register_to_config(init):
+        sig = inspect.signature(init)
+
+        def wrapped(self, *a, **k):
+            bound = sig.bind(self, *a, **k)
+            bound.apply_defaults()
+            cfg = {n: v for n, v in bound.arguments.items() if n != "self"}
+            self.config = _Cfg(cfg)
+            init(self, *a, **k)
+        return wrapped
+
+    cu.ConfigMixin, cu.register_to_config = ConfigMixin, register_to_config
+    sch = types.ModuleType("diffusers.schedulers")
+    su = types.ModuleType("diffusers.schedulers.scheduling_utils")
+    ut = types.ModuleType("diffusers.utils")
+
+    class SchedulerOutput:
+        def __init__(self, prev_sample):
+            self.prev_sample = prev_sample
+
+    import enum
+    su.KarrasDiffusionSchedulers = enum.Enum("KarrasDiffusionSchedulers", ["UniPCMultistepScheduler"])
+    su.SchedulerMixin = type("SchedulerMixin", (), {})
+    su.SchedulerOutput = SchedulerOutput
+    ut.deprecate = lambda *a, **k: None
+    ut.is_scipy_available = lambda: False
+    sys.modules.update({"diffusers.schedulers": sch, "diffusers.schedulers.scheduling_utils": su, "diffusers.utils": ut})
+    spec = importlib.util.spec_from_file_location(name, os.path.join(REF, "diffusers_lite/wan/utils/fm_solvers_unipc.py"))
+    mod = importlib.util.module_from_spec(spec)
+    sys.modules[name] = mod
+    spec.loader.exec_module(mod)
+    return mod

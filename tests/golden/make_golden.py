@@ -171,10 +171,62 @@ def case_a2a(name, world=2):
     print(name, "ok")
 
 
+def case_unipc(name):
+    """the reference FlowUniPCMultistepScheduler (fm_solvers_unipc.py) driven the way train_step_refl does
+    (train_prfl.py:631-735): set_timesteps(40, shift), m no-grad steps, one step with autograd through the model output,
+    then the PRFL loss glue.  The 'model' is oracle.unipc_oracle.toy_velocity (seeded weights)."""
+    from oracle.unipc_oracle import toy_velocity
+    S = ref_shim.load_scheduler()
+    g = torch.Generator().manual_seed(70)
+    shape = (1, 8, 2, 4, 6)
+    x_init = torch.randn(shape, generator=g)
+    w = torch.randn(shape, generator=g) * 0.5
+    fx = dict(shape=shape, seed=70, chains={})
+    for steps, shift, solver_type, order in [(40, 3.0, "bh2", 2), (40, 5.0, "bh2", 2), (12, 3.0, "bh1", 3), (8, 1.0, "bh2", 1)]:
+        sch = S.FlowUniPCMultistepScheduler(num_train_timesteps=1000, shift=1, use_dynamic_shifting=False,
+                                            solver_type=solver_type, solver_order=order)
+        sch.set_timesteps(steps, device="cpu", shift=shift)
+        x = x_init.clone()
+        traj, x0s = [], []
+        with torch.no_grad():
+            for t in sch.timesteps:
+                v = toy_velocity(x, t, w)
+                x = sch.step(v, t, x, return_dict=False)[0]
+                traj.append(x.clone())
+                x0s.append(sch.model_outputs[-1].clone())
+        fx["chains"][(steps, shift, solver_type, order)] = dict(timesteps=sch.timesteps.clone(), sigmas=sch.sigmas.clone(),
+                                                                traj=traj, x0=x0s)
+    # PRFL-shaped: m no-grad steps, then a differentiable step; gradient w.r.t. the toy model weight and the latent
+    grads = {}
+    for m in (0, 1, 7, 38):
+        sch = S.FlowUniPCMultistepScheduler(num_train_timesteps=1000, shift=1, use_dynamic_shifting=False)
+        sch.set_timesteps(40, device="cpu", shift=3.0)
+        x = x_init.clone()
+        with torch.no_grad():
+            for i in range(m):
+                t = sch.timesteps[i]
+                x = sch.step(toy_velocity(x, t, w), t, x, return_dict=False)[0]
+        wg = w.clone().requires_grad_(True)
+        xg = x.clone().requires_grad_(True)
+        t_mid = sch.timesteps[m]
+        prev = sch.step(toy_velocity(xg, t_mid, wg), t_mid, xg, return_dict=False)[0]
+        reward = torch.tanh(prev.mean(dim=(1, 2, 3, 4)) * 5.0)        # stand-in for the reward model (|r| < 1: loss active)
+        loss = 0.1 * torch.relu(-reward.squeeze() + 2).mean()       # train_prfl.py:796-798
+        loss.backward()
+        grads[m] = dict(prev=prev.detach().clone(), loss=loss.detach().clone(), grad_w=wg.grad.clone(), grad_x=xg.grad.clone())
+    fx["prfl"] = grads
+    torch.save(fx, os.path.join(HERE, name + ".pt"))
+    print(name, "ok", {k: float(v["loss"]) for k, v in grads.items()})
+
+
 if __name__ == "__main__":
     assert ref_shim.available(), "needs the reference checkout"
     torch.set_num_threads(8)
     M, N = ref_shim.load()
+    if len(sys.argv) > 1 and sys.argv[1] == "unipc":      # regenerate only the scheduler fixture
+        case_unipc("unipc")
+        sys.exit(0)
+    case_unipc("unipc")
     case_ops(M, "ops")
     case_model(M, "tiny_t2v", synth.tiny_cfg("t2v"), (5, 12, 20), 10, 11, [1, 2])
     case_model(M, "tiny_i2v", synth.tiny_cfg("i2v"), (3, 10, 14), 20, 21, [2])

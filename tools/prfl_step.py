@@ -3,7 +3,7 @@ depth that fits one GPU with fp32 master weights + fp32 gradients:
 
   1. `m` no-grad DiT forwards of the trainable video model (VGM, `--blocks` Wan-14B blocks)      [train_prfl.py:665-699]
   2. one forward WITH grad (per-block recompute in backward)                                      [:723-725]
-  3. a differentiable scheduler step latent' = latent - dt * noise_pred (stand-in for UniPC.step, out of scope) [:734]
+  3. the differentiable FlowUniPC scheduler step (prfl_b200.scheduler, one fused kernel)           [:734]
   4. frozen reward model: 8-block Wan-14B features -> QueryAttention -> MLP -> loss 0.1*relu(2 - r) [:764-798]
   5. backward through 4 -> 3 -> 2 (dgrad only through the reward model; its weight grads are never used, Appendix B.10)
 
@@ -69,7 +69,10 @@ def main():
         mask = torch.zeros(4, fr, hh, ww, device=dev)
         mask[:, 0] = 1.0                                            # train_prfl.py:537-542
         extra = dict(clip_fea=torch.randn(1, 257, 1280, device=dev), y=[torch.cat([mask, torch.randn(16, fr, hh, ww, device=dev)])])
-    dt = 0.025
+    from prfl_b200.prfl import refl_chain
+    from prfl_b200.scheduler import FlowUniPCMultistepScheduler
+    sched = FlowUniPCMultistepScheduler(num_train_timesteps=1000, shift=1, use_dynamic_shifting=False)   # train_prfl.py:411-413
+    cond = dict(image_embeds=extra.get("clip_fea"), latents_condition=torch.stack(extra["y"]) if args.i2v else None)
 
     def ev():
         e = torch.cuda.Event(enable_timing=True)
@@ -77,22 +80,9 @@ def main():
         return e
 
     def one_step():
-        marks = {"start": ev()}
-        lat = latent
-        with torch.no_grad():
-            for i in range(args.m):
-                t = torch.tensor([999.0 - 25 * i], device=dev)
-                pred = vgm(x=[lat], t=t, context=ctx, seq_len=L, **extra)[0]
-                lat = lat - dt * pred
-        marks["nograd_done"] = ev()
-        t = torch.tensor([999.0 - 25 * args.m], device=dev)
-        pred = vgm(x=[lat], t=t, context=ctx, seq_len=L, **extra)[0]
-        marks["grad_fwd_done"] = ev()
-        lat2 = lat - dt * pred
-        feats = torch.stack(lrm(x=[lat2], t=t - 25, context=ctx, seq_len=L, output_features=True, selected_layers=[8], **extra))
-        reward = mlp(qa(feats))
-        loss = 0.1 * torch.relu(2.0 - reward).mean()
-        marks["lrm_fwd_done"] = ev()
+        marks = {}
+        loss, _ = refl_chain(vgm, lrm, qa, mlp, sched, latent[None], torch.stack(ctx), L, args.m, flow_shift=5.0,
+                             feature_layer=[8], marks=marks, **cond)
         loss.backward()
         marks["bwd_done"] = ev()
         if opt is not None:
