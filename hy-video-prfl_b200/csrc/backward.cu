@@ -1,5 +1,5 @@
 // Memory-bound backward kernels of the Wan-DiT block: LayerNorm(+modulate/affine) backward, RMSNorm(+RoPE)
-// backward (row kernels: one warp per row, shuffle reductions) and the token-dimension reductions that produce
+// backward (row kernels: one 4-warp CTA per row, shuffle + shared-memory reductions) and the token-dimension reductions that produce
 // bias / modulation / gate / norm-weight gradients (column kernels: a CTA owns 256 columns x a chunk of rows and
 // writes one partial row; the [nparts, N] partials are summed by the caller).
 #include "common.cuh"
@@ -7,6 +7,20 @@
 namespace prfl {
 
 constexpr int COL_ROWS = 256;   // rows per partial
+
+// Row kernels here: one CTA (4 warps) per row, thread t owns the 8-channel pieces t, t+128, ... (PER = ceil(C/1024) of
+// them).  The whole row payload then fits in a few dozen registers per thread (the earlier one-warp-per-row form needed
+// 160+ registers at C = 5120 and ptxas spilled the row to local memory: 570 GB/s), every global access is one coalesced
+// 16/32-byte piece per thread, and each row costs two block reductions through shared memory.
+__device__ __forceinline__ float2 block_sum2(float2 v, float2* red /*[2][4]*/, int phase) {
+  v.x = warp_sum(v.x);
+  v.y = warp_sum(v.y);
+  float2* r = red + (phase & 1) * 4;
+  if ((threadIdx.x & 31) == 0) r[threadIdx.x >> 5] = v;
+  __syncthreads();
+  const float2 a = r[0], b = r[1], c = r[2], d = r[3];
+  return make_float2((a.x + b.x) + (c.x + d.x), (a.y + b.y) + (c.y + d.y));
+}
 
 // =============================================================================================
 // LayerNorm backward:  y = ((x-mean)*rstd [*gamma + beta]) [* (1+scale) + shift]
@@ -17,72 +31,61 @@ __global__ void __launch_bounds__(128) ln_mod_bwd_kernel(const float* __restrict
                                                          const float* __restrict__ scale, const float* __restrict__ gamma,
                                                          const float* __restrict__ mean, const float* __restrict__ rstd,
                                                          float* __restrict__ dx, int64_t rows) {
-  constexpr int C = NCH * 256;
-  const int lane = threadIdx.x & 31;
-  const int64_t warp_global = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
-  for (int64_t row = warp_global; row < rows; row += nwarps) {
+  constexpr int C = NCH * 256, NPIECE = NCH * 32, PER = (NPIECE + 127) / 128;
+  __shared__ float2 red[8];
+  int phase = 0;
+  for (int64_t row = blockIdx.x; row < rows; row += gridDim.x) {
     const float mu = mean[row], rs = rstd[row];
     const float* xr = x + row * C;
     const __nv_bfloat16* dyr = dy + row * C;
-    uint4 graw[NCH];
-#pragma unroll
-    for (int i = 0; i < NCH; ++i) graw[i] = ldg_nc_v4(dyr + 8 * (lane + 32 * i));
+    float g[PER][8], xh[PER][8];
     float s1 = 0.f, s2 = 0.f;
 #pragma unroll
-    for (int i = 0; i < NCH; ++i) {
-      const int c0 = 8 * (lane + 32 * i);
-      const float4 a = __ldg(reinterpret_cast<const float4*>(xr + c0)), b = __ldg(reinterpret_cast<const float4*>(xr + c0) + 1);
-      const float xv[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
-      const uint32_t u[4] = {graw[i].x, graw[i].y, graw[i].z, graw[i].w};
-      float g[8];
+    for (int i = 0; i < PER; ++i) {
+      const int pc = threadIdx.x + 128 * i;
+      if (NPIECE % 128 != 0 && pc >= NPIECE) {
 #pragma unroll
-      for (int j = 0; j < 4; ++j) { g[2 * j] = bf16lo(u[j]); g[2 * j + 1] = bf16hi(u[j]); }
+        for (int j = 0; j < 8; ++j) g[i][j] = xh[i][j] = 0.f;
+        continue;
+      }
+      const int c0 = 8 * pc;
+      const uint4 gr = ldg_nc_v4(dyr + c0);
+      const float4 a = __ldcs(reinterpret_cast<const float4*>(xr + c0)), b = __ldcs(reinterpret_cast<const float4*>(xr + c0) + 1);
+      const float xv[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+      const uint32_t u[4] = {gr.x, gr.y, gr.z, gr.w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) { g[i][2 * j] = bf16lo(u[j]); g[i][2 * j + 1] = bf16hi(u[j]); }
       if (scale) {
         const float4 p = __ldg(reinterpret_cast<const float4*>(scale + c0)), q = __ldg(reinterpret_cast<const float4*>(scale + c0) + 1);
         const float sv[8] = {p.x, p.y, p.z, p.w, q.x, q.y, q.z, q.w};
 #pragma unroll
-        for (int j = 0; j < 8; ++j) g[j] *= 1.f + sv[j];
+        for (int j = 0; j < 8; ++j) g[i][j] *= 1.f + sv[j];
       }
       if (gamma) {
         const float4 p = __ldg(reinterpret_cast<const float4*>(gamma + c0)), q = __ldg(reinterpret_cast<const float4*>(gamma + c0) + 1);
         const float gv[8] = {p.x, p.y, p.z, p.w, q.x, q.y, q.z, q.w};
 #pragma unroll
-        for (int j = 0; j < 8; ++j) g[j] *= gv[j];
+        for (int j = 0; j < 8; ++j) g[i][j] *= gv[j];
       }
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
-        s1 += g[j];
-        s2 += g[j] * (xv[j] - mu) * rs;
+        xh[i][j] = (xv[j] - mu) * rs;
+        s1 += g[i][j];
+        s2 += g[i][j] * xh[i][j];
       }
     }
-    const float c1 = warp_sum(s1) * (1.0f / C), c2 = warp_sum(s2) * (1.0f / C);
+    const float2 tot = block_sum2(make_float2(s1, s2), red, phase++);
+    const float c1 = tot.x * (1.0f / C), c2 = tot.y * (1.0f / C);
     float* dxr = dx + row * C;
 #pragma unroll
-    for (int i = 0; i < NCH; ++i) {
-      const int c0 = 8 * (lane + 32 * i);
-      const float4 a = __ldg(reinterpret_cast<const float4*>(xr + c0)), b = __ldg(reinterpret_cast<const float4*>(xr + c0) + 1);
-      const float xv[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
-      const uint32_t u[4] = {graw[i].x, graw[i].y, graw[i].z, graw[i].w};
-      float g[8];
-#pragma unroll
-      for (int j = 0; j < 4; ++j) { g[2 * j] = bf16lo(u[j]); g[2 * j + 1] = bf16hi(u[j]); }
-      if (scale) {
-        const float4 p = __ldg(reinterpret_cast<const float4*>(scale + c0)), q = __ldg(reinterpret_cast<const float4*>(scale + c0) + 1);
-        const float sv[8] = {p.x, p.y, p.z, p.w, q.x, q.y, q.z, q.w};
-#pragma unroll
-        for (int j = 0; j < 8; ++j) g[j] *= 1.f + sv[j];
-      }
-      if (gamma) {
-        const float4 p = __ldg(reinterpret_cast<const float4*>(gamma + c0)), q = __ldg(reinterpret_cast<const float4*>(gamma + c0) + 1);
-        const float gv[8] = {p.x, p.y, p.z, p.w, q.x, q.y, q.z, q.w};
-#pragma unroll
-        for (int j = 0; j < 8; ++j) g[j] *= gv[j];
-      }
+    for (int i = 0; i < PER; ++i) {
+      const int pc = threadIdx.x + 128 * i;
+      if (NPIECE % 128 != 0 && pc >= NPIECE) continue;
+      const int c0 = 8 * pc;
       float4 d0 = *reinterpret_cast<const float4*>(dxr + c0), d1 = *(reinterpret_cast<const float4*>(dxr + c0) + 1);
       float o[8] = {d0.x, d0.y, d0.z, d0.w, d1.x, d1.y, d1.z, d1.w};
 #pragma unroll
-      for (int j = 0; j < 8; ++j) o[j] += rs * (g[j] - c1 - (xv[j] - mu) * rs * c2);
+      for (int j = 0; j < 8; ++j) o[j] += rs * (g[i][j] - c1 - xh[i][j] * c2);
       *reinterpret_cast<float4*>(dxr + c0) = make_float4(o[0], o[1], o[2], o[3]);
       *(reinterpret_cast<float4*>(dxr + c0) + 1) = make_float4(o[4], o[5], o[6], o[7]);
     }
@@ -101,28 +104,28 @@ __global__ void __launch_bounds__(128) rmsnorm_rope_bwd_kernel(const __nv_bfloat
                                                                __nv_bfloat16* __restrict__ dx, int64_t lddx,
                                                                __nv_bfloat16* __restrict__ gw, int64_t ldgw, int64_t rows,
                                                                int64_t n_rot, int64_t pos0) {
-  constexpr int C = NCH * 256;
-  const int lane = threadIdx.x & 31;
-  const int64_t warp_global = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
-  for (int64_t row = warp_global; row < rows; row += nwarps) {
+  constexpr int C = NCH * 256, NPIECE = NCH * 32, PER = (NPIECE + 127) / 128;
+  __shared__ float2 red[8];
+  int phase = 0;
+  for (int64_t row = blockIdx.x; row < rows; row += gridDim.x) {
     const float rs = rstd[row];
-    uint4 xraw[NCH], graw[NCH];
-#pragma unroll
-    for (int i = 0; i < NCH; ++i) {
-      xraw[i] = ldg_nc_v4(x + row * ldx + 8 * (lane + 32 * i));
-      graw[i] = ldg_nc_v4(dy + row * lddy + 8 * (lane + 32 * i));
-    }
     const bool rot = cos_tab != nullptr && row < n_rot;
     const float* cr = rot ? cos_tab + (pos0 + row) * 64 : nullptr;
     const float* sr = rot ? sin_tab + (pos0 + row) * 64 : nullptr;
+    float dn[PER][8], xh[PER][8];      // dn = un-rotated dy (dt); xh = x * rstd
     float acc = 0.f;
-    // pass 1: un-rotate dy in place (kept packed as fp32 pairs would need 2x registers, so recompute in pass 2)
 #pragma unroll
-    for (int i = 0; i < NCH; ++i) {
-      const int c0 = 8 * (lane + 32 * i);
-      const uint32_t ux[4] = {xraw[i].x, xraw[i].y, xraw[i].z, xraw[i].w};
-      const uint32_t ug[4] = {graw[i].x, graw[i].y, graw[i].z, graw[i].w};
+    for (int i = 0; i < PER; ++i) {
+      const int pc = threadIdx.x + 128 * i;
+      if (NPIECE % 128 != 0 && pc >= NPIECE) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) dn[i][j] = xh[i][j] = 0.f;
+        continue;
+      }
+      const int c0 = 8 * pc;
+      const uint4 xraw = ldg_nc_v4(x + row * ldx + c0), graw = ldg_nc_v4(dy + row * lddy + c0);
+      const uint32_t ux[4] = {xraw.x, xraw.y, xraw.z, xraw.w};
+      const uint32_t ug[4] = {graw.x, graw.y, graw.z, graw.w};
       const float4 w0 = __ldg(reinterpret_cast<const float4*>(w + c0)), w1 = __ldg(reinterpret_cast<const float4*>(w + c0) + 1);
       const float wv[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
       float cc[4] = {1.f, 1.f, 1.f, 1.f}, sn[4] = {0.f, 0.f, 0.f, 0.f};
@@ -135,36 +138,26 @@ __global__ void __launch_bounds__(128) rmsnorm_rope_bwd_kernel(const __nv_bfloat
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         const float gr = bf16lo(ug[j]), gi = bf16hi(ug[j]);
-        const float dtr = gr * cc[j] + gi * sn[j], dti = -gr * sn[j] + gi * cc[j];
-        const float xr_ = bf16lo(ux[j]) * rs, xi_ = bf16hi(ux[j]) * rs;
-        acc += dtr * wv[2 * j] * xr_ + dti * wv[2 * j + 1] * xi_;
+        dn[i][2 * j] = gr * cc[j] + gi * sn[j];
+        dn[i][2 * j + 1] = -gr * sn[j] + gi * cc[j];
+        xh[i][2 * j] = bf16lo(ux[j]) * rs;
+        xh[i][2 * j + 1] = bf16hi(ux[j]) * rs;
+        acc += dn[i][2 * j] * wv[2 * j] * xh[i][2 * j] + dn[i][2 * j + 1] * wv[2 * j + 1] * xh[i][2 * j + 1];
       }
     }
-    const float c2 = warp_sum(acc) * (1.0f / C);
+    const float c2 = block_sum2(make_float2(acc, 0.f), red, phase++).x * (1.0f / C);
 #pragma unroll
-    for (int i = 0; i < NCH; ++i) {
-      const int c0 = 8 * (lane + 32 * i);
-      const uint32_t ux[4] = {xraw[i].x, xraw[i].y, xraw[i].z, xraw[i].w};
-      const uint32_t ug[4] = {graw[i].x, graw[i].y, graw[i].z, graw[i].w};
+    for (int i = 0; i < PER; ++i) {
+      const int pc = threadIdx.x + 128 * i;
+      if (NPIECE % 128 != 0 && pc >= NPIECE) continue;
+      const int c0 = 8 * pc;
       const float4 w0 = __ldg(reinterpret_cast<const float4*>(w + c0)), w1 = __ldg(reinterpret_cast<const float4*>(w + c0) + 1);
       const float wv[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
-      float cc[4] = {1.f, 1.f, 1.f, 1.f}, sn[4] = {0.f, 0.f, 0.f, 0.f};
-      if (rot) {
-        const int j0 = (c0 & 127) >> 1;
-        const float4 cv = __ldg(reinterpret_cast<const float4*>(cr + j0)), sv = __ldg(reinterpret_cast<const float4*>(sr + j0));
-        cc[0] = cv.x; cc[1] = cv.y; cc[2] = cv.z; cc[3] = cv.w;
-        sn[0] = sv.x; sn[1] = sv.y; sn[2] = sv.z; sn[3] = sv.w;
-      }
       float od[8], og[8];
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const float gr = bf16lo(ug[j]), gi = bf16hi(ug[j]);
-        const float dtr = gr * cc[j] + gi * sn[j], dti = -gr * sn[j] + gi * cc[j];
-        const float xr_ = bf16lo(ux[j]) * rs, xi_ = bf16hi(ux[j]) * rs;
-        og[2 * j] = dtr * bf16_round(xr_);
-        og[2 * j + 1] = dti * bf16_round(xi_);
-        od[2 * j] = rs * (dtr * wv[2 * j] - xr_ * c2);
-        od[2 * j + 1] = rs * (dti * wv[2 * j + 1] - xi_ * c2);
+      for (int j = 0; j < 8; ++j) {
+        og[j] = dn[i][j] * bf16_round(xh[i][j]);
+        od[j] = rs * (dn[i][j] * wv[j] - xh[i][j] * c2);
       }
       uint4 o;
       o.x = pack_bf16x2(od[0], od[1]); o.y = pack_bf16x2(od[2], od[3]);
@@ -259,9 +252,9 @@ static int dispatch_nch_b(int C, F&& f) {
   }
 }
 
-static inline int row_grid_b(int64_t rows) {
-  int64_t need = (rows + 3) / 4, cap = (int64_t)sm_count() * 8;
-  return (int)(need < cap ? (need > 0 ? need : 1) : cap);
+static inline int row_grid_b(int64_t rows) {   // one CTA per row, grid-stride; up to 16 resident CTAs of 4 warps per SM
+  int64_t cap = (int64_t)sm_count() * 16;
+  return (int)(rows < cap ? (rows > 0 ? rows : 1) : cap);
 }
 static inline bool al16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 

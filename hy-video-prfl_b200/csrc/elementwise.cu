@@ -1,14 +1,23 @@
 // Memory-bound kernels of the Wan-DiT block: LayerNorm+AdaLN modulate, RMSNorm+3-D RoPE, casts,
-// patchify / unpatchify.  All are HBM-bound: one warp owns one row, the whole row lives in
+// patchify / unpatchify.  All are HBM-bound: one 4-warp CTA owns one row, the whole row lives in
 // registers between its single 128-bit-vectorised read and its single write, reductions are
-// warp shuffles.  Roofline per row (C channels): ln_mod fwd 4C read + 2C written; rmsnorm_rope
+// warp shuffles + one shared-memory exchange.  Roofline per row (C channels): ln_mod fwd 4C read + 2C written; rmsnorm_rope
 // 2C + 2C (+ 512 B of cos/sin).
 #include "common.cuh"
 
 namespace prfl {
 
-// Lane `l` of the warp owns channels [8*(l + 32*i), 8*(l + 32*i) + 8) for i < NCH  (NCH = C/256).
-// Every load/store instruction of the warp therefore touches 32 consecutive 16- or 32-byte pieces.
+// Row kernels: one CTA (4 warps) per row, thread t owns the 8-channel pieces t, t+128, ... (PER = ceil(C/1024)).  The row
+// payload is a few dozen registers per thread (the one-warp-per-row form needed 226-255 registers at C = 5120, i.e. 8
+// warps per SM), every load/store instruction of a warp touches 32 consecutive 16- or 32-byte pieces, and a row costs
+// one or two block reductions through shared memory.
+__device__ __forceinline__ float block_sum(float v, float* red /*[2][4]*/, int phase) {
+  v = warp_sum(v);
+  float* r = red + (phase & 1) * 4;
+  if ((threadIdx.x & 31) == 0) r[threadIdx.x >> 5] = v;
+  __syncthreads();
+  return (r[0] + r[1]) + (r[2] + r[3]);
+}
 
 // =============================================================================================
 // LayerNorm + modulate   (model.py:125-135, 345, 352, 353)
@@ -20,43 +29,50 @@ __global__ void __launch_bounds__(128) ln_mod_fwd_kernel(const float* __restrict
                                                          float* __restrict__ mean_out, float* __restrict__ rstd_out,
                                                          int64_t rows, float eps, int round_bf16,
                                                          __nv_bfloat16* __restrict__ out_lo = nullptr) {
-  constexpr int C = NCH * 256;
-  const int lane = threadIdx.x & 31;
-  const int64_t warp_global = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
-  for (int64_t row = warp_global; row < rows; row += nwarps) {
+  constexpr int C = NCH * 256, NPIECE = NCH * 32, PER = (NPIECE + 127) / 128;
+  __shared__ float red[8];
+  int phase = 0;
+  for (int64_t row = blockIdx.x; row < rows; row += gridDim.x) {
     const float* xr = x + row * C;
-    float v[NCH][8];
-#pragma unroll
-    for (int i = 0; i < NCH; ++i) {
-      const float4* p = reinterpret_cast<const float4*>(xr + 8 * (lane + 32 * i));
-      float4 a = __ldcs(p), b = __ldcs(p + 1);
-      v[i][0] = a.x; v[i][1] = a.y; v[i][2] = a.z; v[i][3] = a.w;
-      v[i][4] = b.x; v[i][5] = b.y; v[i][6] = b.z; v[i][7] = b.w;
-    }
+    float v[PER][8];
     float s = 0.f;
 #pragma unroll
-    for (int i = 0; i < NCH; ++i)
+    for (int i = 0; i < PER; ++i) {
+      const int pc = threadIdx.x + 128 * i;
+      const bool ok = NPIECE % 128 == 0 || pc < NPIECE;
+      float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a;
+      if (ok) {
+        const float4* p = reinterpret_cast<const float4*>(xr + 8 * pc);
+        a = __ldcs(p);
+        b = __ldcs(p + 1);
+      }
+      v[i][0] = a.x; v[i][1] = a.y; v[i][2] = a.z; v[i][3] = a.w;
+      v[i][4] = b.x; v[i][5] = b.y; v[i][6] = b.z; v[i][7] = b.w;
 #pragma unroll
       for (int j = 0; j < 8; ++j) s += v[i][j];
-    const float mean = warp_sum(s) * (1.0f / C);
+    }
+    const float mean = block_sum(s, red, phase++) * (1.0f / C);
     float q = 0.f;
 #pragma unroll
-    for (int i = 0; i < NCH; ++i)
+    for (int i = 0; i < PER; ++i) {
+      const bool ok = NPIECE % 128 == 0 || threadIdx.x + 128 * i < NPIECE;
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
-        float d = v[i][j] - mean;
-        q += d * d;
+        const float d = v[i][j] - mean;
+        q += ok ? d * d : 0.f;
       }
-    const float rstd = rsqrtf(warp_sum(q) * (1.0f / C) + eps);
-    if (lane == 0) {
+    }
+    const float rstd = rsqrtf(block_sum(q, red, phase++) * (1.0f / C) + eps);
+    if (threadIdx.x == 0) {
       if (mean_out) mean_out[row] = mean;
       if (rstd_out) rstd_out[row] = rstd;
     }
     __nv_bfloat16* orow = out + row * C;
 #pragma unroll
-    for (int i = 0; i < NCH; ++i) {
-      const int c0 = 8 * (lane + 32 * i);
+    for (int i = 0; i < PER; ++i) {
+      const int pc = threadIdx.x + 128 * i;
+      if (NPIECE % 128 != 0 && pc >= NPIECE) continue;
+      const int c0 = 8 * pc;
       float y[8];
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
@@ -102,18 +118,17 @@ __global__ void __launch_bounds__(128) rmsnorm_rope_fwd_kernel(const __nv_bfloat
                                                                const float* __restrict__ sin_tab, __nv_bfloat16* __restrict__ out,
                                                                int64_t ldo, float* __restrict__ rstd_out, int64_t rows,
                                                                int64_t n_rot, int64_t pos0, float eps) {
-  constexpr int C = NCH * 256;
-  const int lane = threadIdx.x & 31;
-  const int64_t warp_global = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
-  for (int64_t row = warp_global; row < rows; row += nwarps) {
+  constexpr int C = NCH * 256, NPIECE = NCH * 32, PER = (NPIECE + 127) / 128;
+  __shared__ float red[8];
+  int phase = 0;
+  for (int64_t row = blockIdx.x; row < rows; row += gridDim.x) {
     const __nv_bfloat16* xr = x + row * ldx;
-    uint4 raw[NCH];
-#pragma unroll
-    for (int i = 0; i < NCH; ++i) raw[i] = ldg_nc_v4(xr + 8 * (lane + 32 * i));
+    uint4 raw[PER];
     float ss = 0.f;
 #pragma unroll
-    for (int i = 0; i < NCH; ++i) {
+    for (int i = 0; i < PER; ++i) {
+      const int pc = threadIdx.x + 128 * i;
+      raw[i] = (NPIECE % 128 == 0 || pc < NPIECE) ? ldg_nc_v4(xr + 8 * pc) : make_uint4(0u, 0u, 0u, 0u);
       const uint32_t u[4] = {raw[i].x, raw[i].y, raw[i].z, raw[i].w};
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
@@ -121,15 +136,17 @@ __global__ void __launch_bounds__(128) rmsnorm_rope_fwd_kernel(const __nv_bfloat
         ss += a * a + b * b;
       }
     }
-    const float rstd = rsqrtf(warp_sum(ss) * (1.0f / C) + eps);
-    if (lane == 0 && rstd_out) rstd_out[row] = rstd;
+    const float rstd = rsqrtf(block_sum(ss, red, phase++) * (1.0f / C) + eps);
+    if (threadIdx.x == 0 && rstd_out) rstd_out[row] = rstd;
     const bool rot = cos_tab != nullptr && row < n_rot;
     const float* cr = rot ? cos_tab + (pos0 + row) * 64 : nullptr;
     const float* sr = rot ? sin_tab + (pos0 + row) * 64 : nullptr;
     __nv_bfloat16* orow = out + row * ldo;
 #pragma unroll
-    for (int i = 0; i < NCH; ++i) {
-      const int c0 = 8 * (lane + 32 * i);
+    for (int i = 0; i < PER; ++i) {
+      const int pc = threadIdx.x + 128 * i;
+      if (NPIECE % 128 != 0 && pc >= NPIECE) continue;
+      const int c0 = 8 * pc;
       const uint32_t u[4] = {raw[i].x, raw[i].y, raw[i].z, raw[i].w};
       float4 w0 = __ldg(reinterpret_cast<const float4*>(w + c0)), w1 = __ldg(reinterpret_cast<const float4*>(w + c0) + 1);
       const float wv[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
@@ -307,10 +324,10 @@ static int dispatch_nch(int C, F&& f) {
   }
 }
 
-static inline int row_grid(int64_t rows, int warps_per_block, int blocks_per_sm) {
-  int64_t need = (rows + warps_per_block - 1) / warps_per_block;
-  int64_t cap = (int64_t)sm_count() * blocks_per_sm;
-  return (int)(need < cap ? (need > 0 ? need : 1) : cap);
+static inline int row_grid(int64_t rows) {
+  // one 4-warp CTA per row, grid-stride; 16 resident CTAs per SM is the hardware ceiling at 128 threads
+  int64_t cap = (int64_t)sm_count() * 16;
+  return (int)(rows < cap ? (rows > 0 ? rows : 1) : cap);
 }
 
 static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
@@ -333,7 +350,7 @@ int prfl_ln_mod_fwd(const float* x, const float* shift, const float* scale, cons
   if (rows == 0) return PRFL_OK;
   return dispatch_nch(C, [&](auto nch) {
     constexpr int NCH = decltype(nch)::value;
-    ln_mod_fwd_kernel<NCH><<<row_grid(rows, 4, 8), 128, 0, (cudaStream_t)stream>>>(
+    ln_mod_fwd_kernel<NCH><<<row_grid(rows), 128, 0, (cudaStream_t)stream>>>(
         x, shift, scale, gamma, beta, (__nv_bfloat16*)out_bf16, mean, rstd, rows, eps, round_bf16);
     count_launch();
     PRFL_LAUNCH_CHECK("ln_mod_fwd");
@@ -352,7 +369,7 @@ int prfl_ln_mod_split_fwd(const float* x, const float* shift, const float* scale
   if (rows == 0) return PRFL_OK;
   return dispatch_nch(C, [&](auto nch) {
     constexpr int NCH = decltype(nch)::value;
-    ln_mod_fwd_kernel<NCH><<<row_grid(rows, 4, 8), 128, 0, (cudaStream_t)stream>>>(
+    ln_mod_fwd_kernel<NCH><<<row_grid(rows), 128, 0, (cudaStream_t)stream>>>(
         x, shift, scale, nullptr, nullptr, (__nv_bfloat16*)out_hi_bf16, nullptr, nullptr, rows, eps, 0, (__nv_bfloat16*)out_lo_bf16);
     count_launch();
     PRFL_LAUNCH_CHECK("ln_mod_split_fwd");
@@ -373,7 +390,7 @@ int prfl_rmsnorm_rope_fwd(const void* x_bf16, int64_t ldx, const float* w, const
   if (rows == 0) return PRFL_OK;
   return dispatch_nch(C, [&](auto nch) {
     constexpr int NCH = decltype(nch)::value;
-    rmsnorm_rope_fwd_kernel<NCH><<<row_grid(rows, 4, 8), 128, 0, (cudaStream_t)stream>>>(
+    rmsnorm_rope_fwd_kernel<NCH><<<row_grid(rows), 128, 0, (cudaStream_t)stream>>>(
         (const __nv_bfloat16*)x_bf16, ldx, w, cos_tab, sin_tab, (__nv_bfloat16*)out_bf16, ldo, rstd, rows, n_rot, pos0, eps);
     count_launch();
     PRFL_LAUNCH_CHECK("rmsnorm_rope_fwd");

@@ -37,6 +37,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--heads", type=int, default=40)
     ap.add_argument("--quick", action="store_true")
+    ap.add_argument("--sections", default="attention,membound,gemm")
     args = ap.parse_args()
     pk = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else {}
     tf_peak, hbm_peak = pk.get("bf16_tflops_sustained", 1400.0), pk.get("hbm_gbs", 6650.0)
@@ -49,6 +50,9 @@ def main():
     H = args.heads
     g = torch.Generator(device="cuda").manual_seed(0)
     Ls = [8192, 32760] if args.quick else [8192, 16384, 32760, 65536, 75600]
+    sections = args.sections.split(",")
+    if "attention" not in sections:
+        Ls = []
     for L in Ls:
         q, k, v, do = (torch.randn(L, H, 128, generator=g, device="cuda").bfloat16() for _ in range(4))
         iters = max(2, int(3e9 / (L * L)))
@@ -75,6 +79,9 @@ def main():
 
     # memory-bound kernels at the 480P token count
     M, C = 32760, 5120
+    if "membound" not in sections:
+        print(json.dumps(res, indent=1))
+        return
     x = torch.randn(M, C, generator=g, device="cuda")
     sh, sc = torch.randn(C, device="cuda"), torch.randn(C, device="cuda") * 0.1
     t = timeit(lambda: ops.ln_mod(x, sh, sc), 20)
@@ -90,12 +97,22 @@ def main():
     dx = torch.zeros(M, C, device="cuda")
     t = timeit(lambda: ops.ln_mod_bwd(x, dy, sc, None, mean, rstd, dx, False), 20)
     res["membound"].append({"kernel": "ln_mod_bwd (dx accumulate)", "bytes": 14 * C * M, "ms": t, "GBps": 14 * C * M / t / 1e6, "frac": 14 * C * M / t / 1e6 / hbm_peak})
+    qkv_g = torch.randn(M, 3 * C, generator=g, device="cuda").bfloat16()
+    rstd_q = torch.rand(M, device="cuda") + 0.5
+    t = timeit(lambda: ops.rmsnorm_rope_bwd_(qkv[:, :C], w, cos, sin, qkv_g[:, :C], rstd_q, M, 0, need_dw=False), 20)
+    res["membound"].append({"kernel": "rmsnorm_rope_bwd (dx in place)", "bytes": 6 * C * M, "ms": t, "GBps": 6 * C * M / t / 1e6, "frac": 6 * C * M / t / 1e6 / hbm_peak})
+    del qkv_g
     wk = torch.randn(8, C, device="cuda") * 0.01
     t = timeit(lambda: ops.sq_pool(x, wk), 20)
     res["membound"].append({"kernel": "sq_pool_fwd (2 passes)", "bytes": 8 * C * M, "ms": t, "GBps": 8 * C * M / t / 1e6, "frac": 8 * C * M / t / 1e6 / hbm_peak})
     t = timeit(lambda: ops.cast_bf16(x), 20)
     res["membound"].append({"kernel": "cast_f32_bf16", "bytes": 6 * C * M, "ms": t, "GBps": 6 * C * M / t / 1e6, "frac": 6 * C * M / t / 1e6 / hbm_peak})
     del qkv, dx, dy
+    for r in res["membound"]:
+        print(json.dumps(r), file=sys.stderr)
+    if "gemm" not in sections:
+        print(json.dumps(res, indent=1))
+        return
 
     # GEMMs of one 14B block at M = 32760
     def gemm_row(name, M_, N_, K_, a_t, b_t, epi):

@@ -29,6 +29,7 @@ def main():
     ap.add_argument("--latent", default="21,60,104")
     ap.add_argument("--steps", type=int, default=2)
     ap.add_argument("--i2v", action="store_true", help="image-to-video architecture (in_dim 36, CLIP tokens, y conditioning)")
+    ap.add_argument("--profile", action="store_true", help="after timing, run one more step under torch.profiler and add a per-kernel table")
     ap.add_argument("--opt", action="store_true", help="also run the sharded-gradient AdamW step (reduce-scatter, clip, update, all-gather)")
     args = ap.parse_args()
     import torch.distributed as dist
@@ -120,6 +121,17 @@ def main():
         "step_tokens_per_s": L * (args.m + 2) / (sum(avg.values()) * 1e-3),   # DiT forwards per step: m no-grad + 1 grad + 1 reward
         "peak_mem_gb": torch.cuda.max_memory_allocated() / 1e9,
     }
+    if args.profile:
+        from torch.profiler import ProfilerActivity, profile
+        with profile(activities=[ProfilerActivity.CUDA]) as prof:
+            one_step()
+            torch.cuda.synchronize()
+        vgm.zero_grad(set_to_none=True)
+        evs = sorted(prof.key_averages(), key=lambda e: -e.device_time_total)
+        tot = sum(e.device_time_total for e in evs)
+        out["kernels"] = [{"name": e.key[:90], "launches": e.count, "total_ms": e.device_time_total / 1e3,
+                           "share": e.device_time_total / tot} for e in evs[:25]]
+        out["kernels_total_ms"] = tot / 1e3
     if int(os.environ.get("RANK", "0")) == 0:
         print(json.dumps(out, indent=1))
     if world > 1:
