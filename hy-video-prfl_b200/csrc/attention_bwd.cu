@@ -333,6 +333,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmR0, const __grid_constant_
             nd = (j & 2) ? make_float2(d4[j >> 2].z, d4[j >> 2].w) : make_float2(d4[j >> 2].x, d4[j >> 2].y);
           }
           const float2 t = ffma2(make_float2(__uint_as_float(xs[j]), __uint_as_float(xs[j + 1])), c2, nl);
+          // all on MUFU: moving 25 % / 50 % of these to the FMA pipe (as the forward does) measured 23.40 / 25.04 ms vs 23.47 ms
           const float2 pr = make_float2(fast_exp2(t.x), fast_exp2(t.y));
           const float2 g = fmul2(pr, fadd2(make_float2(__uint_as_float(ys[j]), __uint_as_float(ys[j + 1])), nd));
           pk[j >> 1] = pack_bf16x2(pr.x, pr.y);
