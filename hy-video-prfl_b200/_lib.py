@@ -49,7 +49,7 @@ _SIGS = {
     "prfl_sq_pool_fwd": (C.c_int, [_p, _p, _p, _p, _p, _i64, _i32, _i32, _p]),
     "prfl_sq_pool_bwd": (C.c_int, [_p, _p, _p, _p, _p, _p, _p, _p, _i64, _i32, _i32, _i32, _p]),
     "prfl_cast_f32_bf16": (C.c_int, [_p, _p, _i64, _p]),
-    "prfl_unipc_step": (C.c_int, [_p, _p, _p, _p, _p, _p, _f32, _p, _p, _p, _p, _p, _i64, _p]),
+    "prfl_unipc_step": (C.c_int, [_p, _p, _p, _f32, _p, _p, _p, _p, _f32, _p, _p, _p, _p, _p, _i64, _p]),
     "prfl_scale2_f32": (C.c_int, [_p, _f32, _p, _f32, _p, _i64, _p]),
     "prfl_a2a_pack": (C.c_int, [_p, _i64, _i64, _p, _i32, _i32, _i32, _i32, _p]),
 }

@@ -3,6 +3,8 @@
 // the UniP predictor as ~25 ATen elementwise launches over latent-sized fp32 tensors with several temporaries; all three
 // are linear in (sample, model_output, last_sample, previous x0 predictions), so the host folds the step's scalars into
 // two coefficient vectors and this kernel reads each input once and writes x0, the corrected sample and the next sample:
+//   v         = v_cond, or v_uncond + guide * (v_cond - v_uncond) when a second model output is given: classifier-free
+//               guidance of the sampling loop (text2video.py:295-296) folded in
 //   x0        = sample - sigma * v                                              (:318-321)
 //   corrected = c[0] last + c[1] x0 + c[2] h0 + c[3] h1 + c[4] h2               (:486-626, only when the corrector runs)
 //   prev      = p[0] (corrected | sample) + p[1] x0 + p[2] h0 + p[3] h1 + p[4] h2   (:350-484)
@@ -13,6 +15,7 @@ namespace prfl {
 
 struct UniPCCoef {
   float sigma;
+  float guide;
   float c[5];
   float p[5];
   int use_corrector;
@@ -20,7 +23,7 @@ struct UniPCCoef {
 
 template <bool VEC>
 __global__ void __launch_bounds__(256) unipc_step_kernel(const float* __restrict__ sample, const float* __restrict__ v,
-                                                         const float* __restrict__ last, const float* __restrict__ h0,
+                                                         const float* __restrict__ v_uncond, const float* __restrict__ last, const float* __restrict__ h0,
                                                          const float* __restrict__ h1, const float* __restrict__ h2,
                                                          float* __restrict__ x0_out, float* __restrict__ corr_out,
                                                          float* __restrict__ prev_out, int64_t n, const UniPCCoef k) {
@@ -44,6 +47,12 @@ __global__ void __launch_bounds__(256) unipc_step_kernel(const float* __restrict
     };
     ld(sample, s);
     ld(v, m);
+    if (v_uncond) {
+      float u[4];
+      ld(v_uncond, u);
+#pragma unroll
+      for (int j = 0; j < W; ++j) m[j] = u[j] + k.guide * (m[j] - u[j]);
+    }
     if (k.use_corrector) ld(last, l);
     if (h0) ld(h0, a0);
     if (h1) ld(h1, a1);
@@ -77,8 +86,9 @@ __global__ void __launch_bounds__(256) scale2_kernel(const float* __restrict__ g
 
 using namespace prfl;
 
-extern "C" int prfl_unipc_step(const float* sample, const float* model_output, const float* last_sample, const float* hist0,
-                               const float* hist1, const float* hist2, float sigma, const float* corr_coef,
+extern "C" int prfl_unipc_step(const float* sample, const float* model_output, const float* model_output_uncond, float guide_scale,
+                               const float* last_sample, const float* hist0, const float* hist1, const float* hist2, float sigma,
+                               const float* corr_coef,
                                const float* pred_coef, float* x0_out, float* corrected_out, float* prev_out, int64_t n,
                                prfl_stream_t stream) {
   PRFL_CHECK_ARCH();
@@ -86,6 +96,7 @@ extern "C" int prfl_unipc_step(const float* sample, const float* model_output, c
   PRFL_REQUIRE(!corr_coef || (last_sample && corrected_out), PRFL_E_SHAPE, "unipc_step: corrector needs last_sample and corrected_out");
   UniPCCoef k;
   k.sigma = sigma;
+  k.guide = guide_scale;
   k.use_corrector = corr_coef != nullptr;
   for (int i = 0; i < 5; ++i) {
     k.c[i] = corr_coef ? corr_coef[i] : 0.f;
@@ -95,7 +106,8 @@ extern "C" int prfl_unipc_step(const float* sample, const float* model_output, c
   const float* hs[3] = {hist0, hist1, hist2};
   for (int i = 0; i < 3; ++i)
     PRFL_REQUIRE(hs[i] || (k.c[2 + i] == 0.f && k.p[2 + i] == 0.f), PRFL_E_SHAPE, "unipc_step: hist%d is NULL but has a coefficient", i);
-  uintptr_t al = reinterpret_cast<uintptr_t>(sample) | reinterpret_cast<uintptr_t>(model_output) | reinterpret_cast<uintptr_t>(last_sample) |
+  uintptr_t al = reinterpret_cast<uintptr_t>(sample) | reinterpret_cast<uintptr_t>(model_output) | reinterpret_cast<uintptr_t>(model_output_uncond) |
+                 reinterpret_cast<uintptr_t>(last_sample) |
                  reinterpret_cast<uintptr_t>(hist0) | reinterpret_cast<uintptr_t>(hist1) | reinterpret_cast<uintptr_t>(hist2) |
                  reinterpret_cast<uintptr_t>(x0_out) | reinterpret_cast<uintptr_t>(corrected_out) | reinterpret_cast<uintptr_t>(prev_out);
   const bool vec = (al & 15) == 0 && (n & 3) == 0;
@@ -103,10 +115,10 @@ extern "C" int prfl_unipc_step(const float* sample, const float* model_output, c
   int64_t blocks = (work + 255) / 256, cap = (int64_t)sm_count() * 8;
   const int grid = (int)(blocks < cap ? blocks : cap);
   if (vec)
-    unipc_step_kernel<true><<<grid, 256, 0, (cudaStream_t)stream>>>(sample, model_output, last_sample, hist0, hist1, hist2, x0_out,
+    unipc_step_kernel<true><<<grid, 256, 0, (cudaStream_t)stream>>>(sample, model_output, model_output_uncond, last_sample, hist0, hist1, hist2, x0_out,
                                                                    corrected_out, prev_out, n, k);
   else
-    unipc_step_kernel<false><<<grid, 256, 0, (cudaStream_t)stream>>>(sample, model_output, last_sample, hist0, hist1, hist2, x0_out,
+    unipc_step_kernel<false><<<grid, 256, 0, (cudaStream_t)stream>>>(sample, model_output, model_output_uncond, last_sample, hist0, hist1, hist2, x0_out,
                                                                     corrected_out, prev_out, n, k);
   count_launch();
   PRFL_LAUNCH_CHECK("unipc_step");

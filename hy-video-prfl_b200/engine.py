@@ -33,7 +33,7 @@ def _f(p):
 # forward
 # ------------------------------------------------------------------------------------------------
 def block_forward(blk, x: torch.Tensor, em: torch.Tensor, ctx: torch.Tensor, seq_len_i: int, grid: Tuple[int, int, int],
-                  first_block: bool, stash: Optional[Dict] = None) -> torch.Tensor:
+                  first_block: bool, stash: Optional[Dict] = None, sample: int = 0) -> torch.Tensor:
     """One sample through one block.  x: [M, C] fp32 (updated in place), em: [6, C] fp32 (modulation + e),
     ctx: [Lc, C] bf16.  With `stash` (a dict) every intermediate the backward needs is kept."""
     sa, ca = blk.self_attn, blk.cross_attn
@@ -119,15 +119,20 @@ def block_forward(blk, x: torch.Tensor, em: torch.Tensor, ctx: torch.Tensor, seq
         groups.append((("k", "v"), ca.norm_k, ctx))
     a2 = None
     cross = []
+    kv_cache = None if keep else ca.__dict__.get("_kv_cache")    # PreparedContext (model.py): K/V of a constant prompt
     for names, norm, c_in in groups:
-        wkv, bkv = ca._kv_operands(names)
-        kv = ops.gemm(c_in, wkv, bias=bkv, epi=ops.EPI_BF16)                                 # [Lc, 2C]
-        k_raw = kv[:, :C].clone() if keep else None
-        rstd_kc = None
-        if keep:
-            _, rstd_kc = ops.rmsnorm_rope_(kv[:, :C], _f(norm.weight), None, None, ca.eps, save_rstd=True)
-        else:
-            ops.rmsnorm_rope_(kv[:, :C], _f(norm.weight), None, None, ca.eps)
+        kv = None if kv_cache is None else kv_cache.get((names, sample))
+        k_raw = rstd_kc = None
+        if kv is None:
+            wkv, bkv = ca._kv_operands(names)
+            kv = ops.gemm(c_in, wkv, bias=bkv, epi=ops.EPI_BF16)                             # [Lc, 2C]
+            k_raw = kv[:, :C].clone() if keep else None
+            if keep:
+                _, rstd_kc = ops.rmsnorm_rope_(kv[:, :C], _f(norm.weight), None, None, ca.eps, save_rstd=True)
+            else:
+                ops.rmsnorm_rope_(kv[:, :C], _f(norm.weight), None, None, ca.eps)
+            if kv_cache is not None:
+                kv_cache[(names, sample)] = kv
         kc, vc = kv[:, :C].unflatten(1, (n, d)), kv[:, C:].unflatten(1, (n, d))
         if keep:
             o_g, lse_g = ops.attn_fwd(q2_3, kc, vc, need_lse=True)

@@ -30,7 +30,7 @@ from . import ops
 from .parallel import get_sequence_parallel_state, nccl_info, ulysses_gather_tokens, ulysses_scatter_tokens, all_gather
 from .rope import rope_tables
 
-__all__ = ["WanModel", "WanAttentionBlock", "WanSelfAttention", "WanT2VCrossAttention", "WanI2VCrossAttention",
+__all__ = ["WanModel", "PreparedContext", "WanAttentionBlock", "WanSelfAttention", "WanT2VCrossAttention", "WanI2VCrossAttention",
            "WanRMSNorm", "WanLayerNorm", "Head", "MLPProj", "sinusoidal_embedding_1d", "rope_params", "rope_apply"]
 
 T5_CONTEXT_TOKEN_NUMBER = 512
@@ -235,11 +235,16 @@ class WanT2VCrossAttention(WanSelfAttention):
         return (cache.get("w" + "".join(names), ws, lambda: _cat_bf16(ws)),
                 cache.get("b" + "".join(names), bs, lambda: _cat_f32(bs)))
 
-    def _attend_ctx(self, q3, ctx, names, norm):
+    def _attend_ctx(self, q3, ctx, names, norm, sample=0):
         C, n, d = self.dim, self.num_heads, self.head_dim
-        wkv, bkv = self._kv_operands(names)
-        kv = ops.gemm(ctx, wkv, bias=bkv, epi=ops.EPI_BF16)                       # [Lc, 2C]
-        ops.rmsnorm_rope_(kv[:, :C], norm.weight.detach().float(), None, None, self.eps)
+        cache = self.__dict__.get("_kv_cache")           # set by WanModel.forward for a PreparedContext (no-grad only)
+        kv = None if cache is None else cache.get((names, sample))
+        if kv is None:
+            wkv, bkv = self._kv_operands(names)
+            kv = ops.gemm(ctx, wkv, bias=bkv, epi=ops.EPI_BF16)                   # [Lc, 2C]
+            ops.rmsnorm_rope_(kv[:, :C], norm.weight.detach().float(), None, None, self.eps)
+            if cache is not None:
+                cache[(names, sample)] = kv
         return ops.attn_fwd(q3, kv[:, :C].unflatten(1, (n, d)), kv[:, C:].unflatten(1, (n, d)))
 
     def attend(self, h, context, context_lens=None):
@@ -251,7 +256,7 @@ class WanT2VCrossAttention(WanSelfAttention):
         for i in range(b):
             q = ops.gemm(h[i], wq, bias=bq, epi=ops.EPI_BF16)
             ops.rmsnorm_rope_(q, self.norm_q.weight.detach().float(), None, None, self.eps)
-            o = self._attend_ctx(q.unflatten(1, (n, d)), context[i], ("k", "v"), self.norm_k)
+            o = self._attend_ctx(q.unflatten(1, (n, d)), context[i], ("k", "v"), self.norm_k, i)
             outs.append(o.reshape(s, C))
         return torch.stack(outs)
 
@@ -280,10 +285,18 @@ class WanI2VCrossAttention(WanT2VCrossAttention):
             q = ops.gemm(h[i], wq, bias=bq, epi=ops.EPI_BF16)
             ops.rmsnorm_rope_(q, self.norm_q.weight.detach().float(), None, None, self.eps)
             q3 = q.unflatten(1, (n, d))
-            o_img = self._attend_ctx(q3, context[i, :n_img].contiguous(), ("k_img", "v_img"), self.norm_k_img)
-            o_txt = self._attend_ctx(q3, context[i, n_img:].contiguous(), ("k", "v"), self.norm_k)
+            o_img = self._attend_ctx(q3, context[i, :n_img].contiguous(), ("k_img", "v_img"), self.norm_k_img, i)
+            o_txt = self._attend_ctx(q3, context[i, n_img:].contiguous(), ("k", "v"), self.norm_k, i)
             outs.append((o_txt + o_img).reshape(s, C))                            # model.py:269 (bf16 add)
         return torch.stack(outs)
+
+
+class PreparedContext:
+    """Opaque result of `WanModel.prepare_context`: embedded context [B, n_ctx, dim] bf16 + per-block K/V cache."""
+
+    def __init__(self, embedded: torch.Tensor):
+        self.embedded = embedded
+        self.kv = {}
 
 
 WAN_CROSSATTENTION_CLASSES = {"t2v_cross_attn": WanT2VCrossAttention, "i2v_cross_attn": WanI2VCrossAttention}
@@ -331,7 +344,7 @@ class WanAttentionBlock(nn.Module):
         ctx = ctx if ctx.dtype == torch.bfloat16 else ctx.to(torch.bfloat16)
         x = x.detach()
         for i in range(x.shape[0]):
-            engine.block_forward(self, x[i], em[i], ctx[i].contiguous(), int(seq_lens[i]), grids[i], first_block_bf16_input)
+            engine.block_forward(self, x[i], em[i], ctx[i].contiguous(), int(seq_lens[i]), grids[i], first_block_bf16_input, sample=i)
         return x
 
 
@@ -473,6 +486,15 @@ class WanModel(nn.Module):
         b = cache.get("bp", [self.patch_embedding.bias], lambda: _cat_f32([self.patch_embedding.bias]))
         return w, b
 
+    @torch.no_grad()
+    def prepare_context(self, context, clip_fea=None) -> "PreparedContext":
+        """Embed a prompt ONCE for many no-grad forwards: the text / CLIP embeddings and, filled lazily
+        by the first forward, every block's cross-attention K / V of the context are constants of the prompt and the
+        weights — the reference recomputes them on every rank, block and call (model.py:206-226, 590-607), i.e. 80-100
+        times per sampled video and m times per PRFL step.  Pass the result as `context=`; results are bit-identical.
+        Valid until the weights change; never used when autograd is recording."""
+        return PreparedContext(self._embed_context(context, clip_fea))
+
     def _embed_context(self, context, clip_fea):
         dev = self.patch_embedding.weight.device
         ctx = torch.stack([torch.cat([u, u.new_zeros(self.text_len - u.size(0), u.size(1))]) for u in context])
@@ -496,8 +518,9 @@ class WanModel(nn.Module):
         """Same contract as the reference (model.py:534-681): x list of [C_in, F, H, W], t [B], context list of
         [L, C]; returns a list of [C_out, F, H, W] fp32 tensors, or with output_features the list of
         [B, L, dim] fp32 features after the selected (1-based) blocks."""
+        prepared = context if isinstance(context, PreparedContext) else None
         if self.model_type in ("i2v", "flf2v"):
-            assert clip_fea is not None and y is not None
+            assert (clip_fea is not None or prepared is not None) and y is not None
         assert not self.enable_teacache, "teacache is an inference-time heuristic outside this path"
         dev = self.patch_embedding.weight.device
         wp, bp = self._patch_operands()
@@ -531,15 +554,21 @@ class WanModel(nn.Module):
         tp = self.time_projection[1]
         e0 = F.linear(F.silu(e), tp.weight.float(), tp.bias.float()).unflatten(1, (6, self.dim))
 
-        ctx = self._embed_context(context, clip_fea)
+        use_kv_cache = prepared is not None and not torch.is_grad_enabled()
+        ctx = prepared.embedded if prepared is not None else self._embed_context(context, clip_fea)
 
         if get_sequence_parallel_state():
             xs = torch.chunk(xs, nccl_info.sp_size, dim=1)[nccl_info.rank_within_group].contiguous()
 
         features_list = []
         for index, block in enumerate(self.blocks):
-            xs = block(xs, e=e0, seq_lens=seq_lens, grid_sizes=grid_sizes, freqs=self.freqs, context=ctx,
-                       context_lens=None, first_block_bf16_input=(index == 0))
+            if use_kv_cache:
+                block.cross_attn.__dict__["_kv_cache"] = prepared.kv.setdefault(index, {})
+            try:
+                xs = block(xs, e=e0, seq_lens=seq_lens, grid_sizes=grid_sizes, freqs=self.freqs, context=ctx,
+                           context_lens=None, first_block_bf16_input=(index == 0))
+            finally:
+                block.cross_attn.__dict__.pop("_kv_cache", None)
             if output_features and index + 1 in selected_layers:
                 if get_sequence_parallel_state():
                     features_list.append(all_gather(xs, dim=1))

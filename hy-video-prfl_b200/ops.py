@@ -375,12 +375,16 @@ def a2a_pack(strided: torch.Tensor, packed: torch.Tensor, P: int, unpack: bool =
 # ------------------------------------------------------------------------------------------------
 # PRFL chain glue (scheduler step)
 # ------------------------------------------------------------------------------------------------
-def unipc_step(sample, model_output, last_sample, hist, sigma: float, corr_coef, pred_coef):
+def unipc_step(sample, model_output, last_sample, hist, sigma: float, corr_coef, pred_coef, model_output_uncond=None,
+               guide_scale: float = 1.0):
     """One fused FlowUniPC update (fm_solvers_unipc.py:655-739).  All tensors fp32, same shape, contiguous.
     hist: previous x0 predictions, newest first (up to 3).  corr_coef: 5 floats or None; pred_coef: 5 floats.
+    With model_output_uncond the velocity is uncond + guide_scale * (model_output - uncond) (text2video.py:295-296).
     Returns (x0, corrected | None, prev)."""
     import ctypes as C
-    for t, n in ((sample, "sample"), (model_output, "model_output")):
+    for t, n in ((sample, "sample"), (model_output, "model_output"), (model_output_uncond, "model_output_uncond")):
+        if t is None:
+            continue
         _req(t, f32, "unipc_step." + n)
         assert t.is_contiguous() and t.shape == sample.shape
     hs = [None, None, None]
@@ -399,8 +403,9 @@ def unipc_step(sample, model_output, last_sample, hist, sigma: float, corr_coef,
         corrected = torch.empty_like(sample)
         cc = (C.c_float * 5)(*[float(c) for c in corr_coef])
     pc = (C.c_float * 5)(*[float(c) for c in pred_coef])
-    check(lib().prfl_unipc_step(_p(sample), _p(model_output), _p(last_sample) if cc is not None else None, _p(hs[0]), _p(hs[1]),
-                                _p(hs[2]), float(sigma), cc, pc, _p(x0), _p(corrected), _p(prev), sample.numel(), _stream()),
+    check(lib().prfl_unipc_step(_p(sample), _p(model_output), _p(model_output_uncond), float(guide_scale),
+                                _p(last_sample) if cc is not None else None, _p(hs[0]), _p(hs[1]), _p(hs[2]), float(sigma), cc, pc,
+                                _p(x0), _p(corrected), _p(prev), sample.numel(), _stream()),
           "prfl_unipc_step")
     return x0, corrected, prev
 

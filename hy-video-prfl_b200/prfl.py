@@ -54,11 +54,16 @@ def refl_chain(transformer, lrm_transformer, query_attention, mlp, noise_schedul
     cond = dict(context=batch2list(text_states), seq_len=max_sequence_length, clip_fea=image_embeds,
                 y=batch2list(latents_condition) if latents_condition is not None else None)
     mark("start")
-    # 1. no-grad denoising to the mid timestep (:665-699)
+    # 1. no-grad denoising to the mid timestep (:665-699); the prompt's embeddings and cross-attention K/V are constants of
+    #    these m forwards (weights only change at optimizer.step), so they are computed once (WanModel.prepare_context)
     with torch.no_grad():
+        if mid_timestep > 0 and hasattr(transformer, "prepare_context"):
+            cond_ng = dict(cond, context=transformer.prepare_context(cond["context"], image_embeds), clip_fea=None)
+        else:
+            cond_ng = cond
         for i in range(mid_timestep):
             t = torch.tensor([host_t[i]], device=dev)
-            noise_pred = list2batch(transformer(x=batch2list(latent), t=t, cond_flag=True, **cond))
+            noise_pred = list2batch(transformer(x=batch2list(latent), t=t, cond_flag=True, **cond_ng))
             latent = noise_scheduler.step(noise_pred, host_t[i], latent, return_dict=False)[0]
     mark("nograd_done")
     # 2. the step whose gradient is kept (:703-725)

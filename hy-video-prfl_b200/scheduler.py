@@ -257,8 +257,11 @@ class FlowUniPCMultistepScheduler:
 
     # ---- the step ----------------------------------------------------------------------------------------
     def step(self, model_output: torch.Tensor, timestep: Union[int, torch.Tensor], sample: torch.Tensor, return_dict: bool = True,
-             generator=None) -> Union[SchedulerOutput, Tuple]:
-        # fm_solvers_unipc.py:655-739
+             generator=None, model_output_uncond: Optional[torch.Tensor] = None, guide_scale: float = 1.0
+             ) -> Union[SchedulerOutput, Tuple]:
+        """fm_solvers_unipc.py:655-739.  Extension (no-grad only): with `model_output_uncond` the classifier-free-guidance
+        combination uncond + guide_scale * (model_output - uncond) of the sampling loop (text2video.py:295-296) is
+        evaluated inside the same kernel instead of as three more elementwise launches."""
         if self.num_inference_steps is None:
             raise ValueError("Number of inference steps is 'None', you need to run 'set_timesteps' after creating the scheduler")
         if self.step_index is None:
@@ -277,9 +280,13 @@ class FlowUniPCMultistepScheduler:
         sm = sample if sample.dtype == torch.float32 else sample.float()
         mo, sm = mo.contiguous(), sm.contiguous()
         if torch.is_grad_enabled() and (mo.requires_grad or sm.requires_grad):
+            if model_output_uncond is not None:
+                raise NotImplementedError("classifier-free guidance inside step() is a no-grad (sampling) feature")
             prev, x0, new_sample = _StepFn.apply(mo, sm, self, coef)
         else:
-            x0, corrected, prev = ops.unipc_step(sm, mo, self.last_sample, self._hist(), coef["sigma"], coef["corr"], coef["pred"])
+            mu = None if model_output_uncond is None else model_output_uncond.float().contiguous()
+            x0, corrected, prev = ops.unipc_step(sm, mo, self.last_sample, self._hist(), coef["sigma"], coef["corr"], coef["pred"],
+                                                 mu, guide_scale)
             new_sample = corrected if corrected is not None else sm
         for k in range(self.config.solver_order - 1):
             self.model_outputs[k] = self.model_outputs[k + 1]

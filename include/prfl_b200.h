@@ -205,14 +205,17 @@ int prfl_a2a_scatter_p2p(const void* strided, int64_t ld_tok, int64_t ld_head, v
  * One FlowUniPCMultistepScheduler.step (diffusers_lite/wan/utils/fm_solvers_unipc.py:655-739: convert_model_output
  * :318-321, UniC corrector :486-626, UniP predictor :350-484; called from train_prfl.py:690,734 and
  * text2video.py:298-303) as one kernel over the latent (all fp32, n elements):
- *   x0        = sample - sigma * model_output
+ *   v         = model_output, or model_output_uncond + guide_scale * (model_output - model_output_uncond) when
+ *               model_output_uncond != NULL (classifier-free guidance, text2video.py:295-296)
+ *   x0        = sample - sigma * v
  *   corrected = c[0] last_sample + c[1] x0 + c[2] hist0 + c[3] hist1 + c[4] hist2      (only if corr_coef != NULL)
  *   prev      = p[0] (corrected | sample) + p[1] x0 + p[2] hist0 + p[3] hist1 + p[4] hist2
  * hist0..2 = the scheduler's previous x0 predictions, newest first (NULL when absent; their coefficients must be 0).
  * corr_coef / pred_coef are HOST arrays of 5 floats folded from the step's sigmas by the caller (scheduler.py). */
-int prfl_unipc_step(const float* sample, const float* model_output, const float* last_sample, const float* hist0,
-                    const float* hist1, const float* hist2, float sigma, const float* corr_coef, const float* pred_coef,
-                    float* x0_out, float* corrected_out, float* prev_out, int64_t n, prfl_stream_t stream);
+int prfl_unipc_step(const float* sample, const float* model_output, const float* model_output_uncond, float guide_scale,
+                    const float* last_sample, const float* hist0, const float* hist1, const float* hist2, float sigma,
+                    const float* corr_coef, const float* pred_coef, float* x0_out, float* corrected_out, float* prev_out,
+                    int64_t n, prfl_stream_t stream);
 /* Backward of the step (it is linear): ya = a * g, yb = b * g (yb may be NULL). */
 int prfl_scale2_f32(const float* g, float a, float* ya, float b, float* yb, int64_t n, prfl_stream_t stream);
 
