@@ -51,6 +51,8 @@ _SIGS = {
     "prfl_cast_f32_bf16": (C.c_int, [_p, _p, _i64, _p]),
     "prfl_unipc_step": (C.c_int, [_p, _p, _p, _f32, _p, _p, _p, _p, _f32, _p, _p, _p, _p, _p, _i64, _p]),
     "prfl_scale2_f32": (C.c_int, [_p, _f32, _p, _f32, _p, _i64, _p]),
+    "prfl_adamw_step": (C.c_int, [_p, _p, _p, _p, _p, _i64, _f32, _f32, _f32, _f32, _f32, _i32, _p]),
+    "prfl_sumsq_f32": (C.c_int, [_p, _i64, _p, _p]),
     "prfl_a2a_pack": (C.c_int, [_p, _i64, _i64, _p, _i32, _i32, _i32, _i32, _p]),
 }
 

@@ -418,3 +418,25 @@ def scale2(g, a: float, b: Optional[float] = None):
     yb = torch.empty_like(g) if b is not None else None
     check(lib().prfl_scale2_f32(_p(g), float(a), _p(ya), float(b or 0.0), _p(yb), g.numel(), _stream()), "prfl_scale2_f32")
     return ya, yb
+
+
+# ------------------------------------------------------------------------------------------------
+# sharded optimizer
+# ------------------------------------------------------------------------------------------------
+def adamw_step_(grad, master, exp_avg, exp_avg_sq, step: int, lr: float, betas, eps: float, weight_decay: float, clip_coef=None):
+    """In-place AdamW on one fp32 shard (all four tensors flat, same length).  clip_coef: 0-dim CUDA fp32 tensor or None."""
+    for t, n in ((grad, "grad"), (master, "master"), (exp_avg, "exp_avg"), (exp_avg_sq, "exp_avg_sq")):
+        _req(t, f32, "adamw_step." + n)
+        assert t.is_contiguous() and t.numel() == master.numel()
+    if clip_coef is not None:
+        _req(clip_coef, f32, "adamw_step.clip_coef")
+    check(lib().prfl_adamw_step(_p(grad), _p(master), _p(exp_avg), _p(exp_avg_sq), _p(clip_coef), master.numel(), float(lr),
+                                float(betas[0]), float(betas[1]), float(eps), float(weight_decay), int(step), _stream()), "prfl_adamw_step")
+
+
+def sumsq_(x, acc):
+    """acc (0-dim CUDA float64) += sum(x^2)."""
+    _req(x, f32, "sumsq.x")
+    _req(acc, torch.float64, "sumsq.acc")
+    check(lib().prfl_sumsq_f32(_p(x.contiguous()), x.numel(), _p(acc), _stream()), "prfl_sumsq_f32")
+    return acc

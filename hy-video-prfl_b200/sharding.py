@@ -156,24 +156,66 @@ class ShardedAdamW:
             s.mul_(coef)
         return norm
 
+    def _grad_norm(self, shards: List[torch.Tensor]) -> torch.Tensor:
+        """Global L2 norm of the sharded gradient, on the device (no host sync)."""
+        if shards[0].is_cuda:
+            from . import ops
+            acc = torch.zeros((), dtype=torch.float64, device=shards[0].device)
+            for s in shards:
+                ops.sumsq_(s, acc)                                   # one pass per shard, double accumulation
+        else:                                                        # CPU tensors: only the world_size-2 gloo tests get here
+            acc = torch.stack([s.double().pow(2).sum() for s in shards]).sum()
+        if self.world > 1:
+            dist.all_reduce(acc, group=self.group)
+        return acc.sqrt().float()
+
     @torch.no_grad()
     def step(self, shards: Optional[List[torch.Tensor]] = None, max_norm: Optional[float] = None):
+        """clip_grad_norm_(max_norm) + AdamW on the shards + all-gather of the updated parameters (train_prfl.py:825-830).
+        On the GPU every unit is one `prfl_adamw_step` launch with the clip coefficient read from device memory."""
         if shards is None:
             shards = self._take_hook_shards() if self._hooks else self.reduce_gradients()
-        norm = self.clip_grad_norm_(shards, max_norm) if max_norm is not None else None
+        norm, coef = None, None
+        if max_norm is not None:
+            norm = self._grad_norm(shards)
+            coef = torch.clamp(max_norm / (norm + 1e-6), max=1.0)
         b1, b2 = self.betas
         for ps, st, g in zip(self.units, self.state, shards):
             st["t"] += 1
             t = st["t"]
             w, m, v = st["master"], st["m"], st["v"]
-            w.mul_(1 - self.lr * self.wd)
-            m.mul_(b1).add_(g, alpha=1 - b1)
-            v.mul_(b2).addcmul_(g, g, value=1 - b2)
-            denom = (v.sqrt() / math.sqrt(1 - b2 ** t)).add_(self.eps)
-            w.addcdiv_(m, denom, value=-self.lr / (1 - b1 ** t))
+            if w.is_cuda:
+                from . import ops
+                ops.adamw_step_(g.contiguous(), w, m, v, t, self.lr, self.betas, self.eps, self.wd, coef)
+            else:                                                    # host-logic path of the gloo tests (torch.optim.AdamW math)
+                if coef is not None:
+                    g = g * coef
+                w.mul_(1 - self.lr * self.wd)
+                m.mul_(b1).add_(g, alpha=1 - b1)
+                v.mul_(b2).addcmul_(g, g, value=1 - b2)
+                denom = (v.sqrt() / math.sqrt(1 - b2 ** t)).add_(self.eps)
+                w.addcdiv_(m, denom, value=-self.lr / (1 - b1 ** t))
             full = self._all_gather(w)
             off = 0
             for p in ps:
                 p.data.copy_(full[off:off + p.numel()].view_as(p))      # bumps p._version => bf16 operand caches refresh
                 off += p.numel()
         return norm
+
+    # -- optimizer state on disk (SURVEY §8f row 3; the reference saves none, train_prfl.py:485-491) ---------------
+    def state_dict(self) -> dict:
+        """This rank's shard of the optimizer state, flat fp32 tensors keyed by unit index (safetensors-friendly)."""
+        out = {}
+        for ui, st in enumerate(self.state):
+            for k in ("master", "m", "v"):
+                out[f"unit{ui:03d}.{k}"] = st[k]
+            out[f"unit{ui:03d}.t"] = torch.tensor([st["t"]], dtype=torch.int64)
+        return out
+
+    def load_state_dict(self, sd: dict):
+        for ui, st in enumerate(self.state):
+            for k in ("master", "m", "v"):
+                src = sd[f"unit{ui:03d}.{k}"]
+                assert src.shape == st[k].shape, (ui, k, src.shape, st[k].shape)
+                st[k].copy_(src)
+            st["t"] = int(sd[f"unit{ui:03d}.t"][0])

@@ -219,6 +219,15 @@ int prfl_unipc_step(const float* sample, const float* model_output, const float*
 /* Backward of the step (it is linear): ya = a * g, yb = b * g (yb may be NULL). */
 int prfl_scale2_f32(const float* g, float a, float* ya, float b, float* yb, int64_t n, prfl_stream_t stream);
 
+/* ---- sharded optimizer ---------------------------------------------------------------------------
+ * AdamW (decoupled weight decay, torch.optim.AdamW semantics; train_prfl.py:482-491, 825-830) on one rank's fp32 shard of
+ * an FSDP unit: grad (already reduce-scattered), master weights and both moments, n elements each, updated in place by
+ * one kernel.  clip_coef_dev: DEVICE pointer to the clip_grad_norm_ coefficient (NULL = 1); step = 1-based update count. */
+int prfl_adamw_step(const float* grad, float* master, float* exp_avg, float* exp_avg_sq, const float* clip_coef_dev, int64_t n,
+                    float lr, float beta1, float beta2, float eps, float weight_decay, int step, prfl_stream_t stream);
+/* acc[0] (DEVICE double) += sum_i x[i]^2 — the local part of FSDP.clip_grad_norm_ (train_prfl.py:825). */
+int prfl_sumsq_f32(const float* x, int64_t n, double* acc, prfl_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -219,6 +219,48 @@ def case_unipc(name):
     print(name, "ok", {k: float(v["loss"]) for k, v in grads.items()})
 
 
+def case_checkpoint(name):
+    """run the UNMODIFIED reference save_checkpoint (diffusers_lite/utils/model_utils.py:70-126) on the
+    tiny T2V model and record what it wrote (directory name, file list, tensor keys, config.json).  Shims: `peft` (unused
+    import) stubbed; FSDP.state_dict_type -> null context, because a single un-wrapped process already holds the full state."""
+    import contextlib
+    import importlib.util
+    import json
+    import tempfile
+    import types
+    from safetensors import safe_open
+    peft = types.ModuleType("peft")
+    peft.get_peft_model_state_dict = lambda *a, **k: {}
+    sys.modules.setdefault("peft", peft)
+    pkg = types.ModuleType("_refutils")
+    pkg.__path__ = [os.path.join(ref_shim.REF, "diffusers_lite/utils")]
+    sys.modules["_refutils"] = pkg
+    tu = types.ModuleType("_refutils.torch_utils")
+    tu.set_logging = lambda *a, **k: None
+    sys.modules["_refutils.torch_utils"] = tu
+    spec = importlib.util.spec_from_file_location("_refutils.model_utils", os.path.join(ref_shim.REF, "diffusers_lite/utils/model_utils.py"))
+    mu = importlib.util.module_from_spec(spec)
+    sys.modules["_refutils.model_utils"] = mu
+    spec.loader.exec_module(mu)
+    mu.FSDP.state_dict_type = staticmethod(lambda *a, **k: contextlib.nullcontext())
+    M, _ = ref_shim.load()
+    cfg = synth.tiny_cfg("t2v")
+    m = ref_model(M, cfg, synth.make_wan_state_dict(cfg, 7))
+    m.config = cfg.kwargs() | {"dtype": "bf16"}
+    with tempfile.TemporaryDirectory() as d:
+        mu.save_checkpoint(m, 0, d, 7)
+        sub = os.listdir(d)
+        assert len(sub) == 1
+        files = sorted(os.listdir(os.path.join(d, sub[0])))
+        with safe_open(os.path.join(d, sub[0], "diffusion_pytorch_model.safetensors"), "pt") as f:
+            keys = sorted(f.keys())
+        config = json.load(open(os.path.join(d, sub[0], "config.json")))
+        back = mu.load_state_dict(os.path.join(d, sub[0]))
+        assert all(torch.equal(back[k], v) for k, v in m.state_dict().items())
+    json.dump({"dir": sub[0], "files": files, "keys": keys, "config": config}, open(os.path.join(HERE, name + ".json"), "w"), indent=1)
+    print(name, sub[0], files, len(keys), "keys")
+
+
 if __name__ == "__main__":
     assert ref_shim.available(), "needs the reference checkout"
     torch.set_num_threads(8)
@@ -226,7 +268,11 @@ if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "unipc":      # regenerate only the scheduler fixture
         case_unipc("unipc")
         sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "checkpoint":
+        case_checkpoint("checkpoint_ref")
+        sys.exit(0)
     case_unipc("unipc")
+    case_checkpoint("checkpoint_ref")
     case_ops(M, "ops")
     case_model(M, "tiny_t2v", synth.tiny_cfg("t2v"), (5, 12, 20), 10, 11, [1, 2])
     case_model(M, "tiny_i2v", synth.tiny_cfg("i2v"), (3, 10, 14), 20, 21, [2])

@@ -340,3 +340,28 @@ def test_head_split_gemm_is_fp32_grade(ops):
     ref = (ref_h.double() @ w.double().t() + bias.double()).float()
     cos, rel = cos_rel(o, ref)
     assert cos > 0.9999999 and rel < 5e-5, (cos, rel)
+
+
+@pytest.mark.parametrize("n", [1024, 1_000_003])
+def test_adamw_step_and_sumsq(ops, n):
+    """prfl_adamw_step against torch.optim.AdamW (same hyper-parameters, 3 steps, with a clip coefficient on the device)
+    and prfl_sumsq_f32 against a float64 torch reduction.  fp32 elementwise: 1e-6 relative."""
+    g = torch.Generator(device="cuda").manual_seed(n)
+    w0 = torch.randn(n, generator=g, device="cuda")
+    ref_p = torch.nn.Parameter(w0.clone())
+    opt = torch.optim.AdamW([ref_p], lr=1e-2, betas=(0.9, 0.95), eps=1e-8, weight_decay=0.05)
+    w, m, v = w0.clone(), torch.zeros(n, device="cuda"), torch.zeros(n, device="cuda")
+    for step in range(1, 4):
+        grad = torch.randn(n, generator=g, device="cuda") * 3.0
+        acc = torch.zeros((), dtype=torch.float64, device="cuda")
+        ops.sumsq_(grad, acc)
+        want = grad.double().pow(2).sum()
+        assert abs(float(acc) - float(want)) <= 1e-9 * float(want)
+        coef = torch.clamp(1.0 / (acc.sqrt().float() + 1e-6), max=1.0)
+        ref_p.grad = grad * coef
+        opt.step()
+        ops.adamw_step_(grad, w, m, v, step, 1e-2, (0.9, 0.95), 1e-8, 0.05, coef)
+        torch.testing.assert_close(w, ref_p.detach(), rtol=2e-6, atol=2e-7)
+        st = opt.state[ref_p]
+        torch.testing.assert_close(m, st["exp_avg"], rtol=2e-6, atol=1e-9)
+        torch.testing.assert_close(v, st["exp_avg_sq"], rtol=2e-6, atol=1e-12)
