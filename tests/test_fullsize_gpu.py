@@ -1,0 +1,108 @@
+"""GPU: size-independent properties at BASELINE.json's FULL sizes (L = 32 760 tokens = 480P x 81f, L = 75 600 = 720P x 81f,
+C = 5 120, ffn 13 824), where the CPU oracle cannot follow.  Each property is something the operator satisfies exactly or
+to a stated rounding bound, whatever the size:
+  attention  : rows of softmax sum to 1 (V = 1 -> O = 1); exact homogeneity in V; key-permutation invariance;
+               identical keys -> uniform attention (O = mean V, dQ = 0); sum_j dV_j = sum_i dO_i; determinism
+  GEMM       : exact homogeneity; a row block of the output does not depend on the other rows
+  row kernels: LayerNorm shift invariance; RoPE preserves the norm of every (2j, 2j+1) pair
+  scheduler  : the last step lands exactly on the x0 prediction (sigma -> 0)
+Heads are cut to 2-4 to keep the runtime in seconds; tile shapes, ragged tails and strides are those of the full problem."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+SIZES = [(32760, 4), (75600, 2)]
+
+
+@pytest.fixture(scope="module")
+def ops():
+    from prfl_b200 import ops as o
+    return o
+
+
+def _qkv(L, H, seed):
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    return tuple(torch.randn(L, H, 128, generator=g, device="cuda").bfloat16() for _ in range(3))
+
+
+@pytest.mark.parametrize("L,H", SIZES)
+def test_attention_forward_properties(ops, L, H):
+    q, k, v = _qkv(L, H, L)
+    o = ops.attn_fwd(q, k, v)
+    assert torch.equal(o, ops.attn_fwd(q, k, v))                                   # deterministic
+    ones = torch.ones_like(v)
+    assert float((ops.attn_fwd(q, k, ones).float() - 1).abs().max()) <= 4e-3         # P rounded to bf16 per element, l in fp32
+    assert torch.equal(ops.attn_fwd(q, k, (2 * v.float()).bfloat16()).float(), 2 * o.float())   # homogeneity in V is exact
+    perm = torch.randperm(L, device="cuda")
+    op = ops.attn_fwd(q, k[perm].contiguous(), v[perm].contiguous())
+    a, b = op.float().flatten(), o.float().flatten()
+    assert float(torch.dot(a, b) / (a.norm() * b.norm())) >= 0.9999                  # summation order only
+
+
+@pytest.mark.parametrize("L,H", SIZES)
+def test_attention_backward_properties(ops, L, H):
+    q, k, v = _qkv(L, H, L + 1)
+    g = torch.Generator(device="cuda").manual_seed(3)
+    do = torch.randn(L, H, 128, generator=g, device="cuda").bfloat16()
+    o, lse = ops.attn_fwd(q, k, v, need_lse=True)
+    dq, dk, dv = ops.attn_bwd(q, k, v, o, do, lse)
+    dq2, dk2, dv2 = ops.attn_bwd(q, k, v, o, do, lse)
+    assert torch.equal(dq, dq2) and torch.equal(dk, dk2) and torch.equal(dv, dv2)    # no atomics: bit-reproducible
+    # sum_j dV_j = sum_i (sum_j P_ij) dO_i = sum_i dO_i
+    want, got = do.float().sum(0), dv.float().sum(0)
+    assert float((got - want).abs().max() / want.abs().max()) <= 2e-2
+    # identical keys: S constant per row -> P uniform -> O = mean(V); dS rows sum to 0 against identical K -> dQ = 0
+    k_same = k[:1].expand(L, H, 128).contiguous()
+    o_u, lse_u = ops.attn_fwd(q, k_same, v, need_lse=True)
+    mean_v = v.float().mean(0, keepdim=True)
+    assert float((o_u.float() - mean_v).abs().max()) <= 2e-3
+    dq_u, _, _ = ops.attn_bwd(q, k_same, v, o_u, do, lse_u)
+    # "0" up to the bf16 rounding of the dS operand (relative 2^-9 per element, summed over L keys)
+    assert float(dq_u.float().abs().max()) <= 1e-2 * float(dq.float().abs().max())
+
+
+def test_gemm_properties_full_size(ops):
+    M, N, K = 32760, 13824, 5120                                                      # ffn.0 of a 14B block at 480P
+    g = torch.Generator(device="cuda").manual_seed(11)
+    a = torch.randn(M, K, generator=g, device="cuda").bfloat16()
+    w = (torch.randn(N, K, generator=g, device="cuda") * 0.02).bfloat16()
+    y = ops.gemm(a, w, epi=ops.EPI_BF16)
+    assert torch.equal(ops.gemm((2 * a.float()).bfloat16(), w, epi=ops.EPI_BF16).float(), 2 * y.float())
+    rows = slice(12345, 12345 + 300)                                                  # straddles tile boundaries, ragged
+    assert torch.equal(ops.gemm(a[rows].contiguous(), w, epi=ops.EPI_BF16), y[rows])
+    ref = (a[rows].float() @ w.float().t())
+    assert float((y[rows].float() - ref).abs().max() / ref.abs().max()) <= 1e-2
+
+
+def test_row_kernel_properties_full_size(ops):
+    from prfl_b200.rope import rope_tables
+    M, C = 32760, 5120
+    g = torch.Generator(device="cuda").manual_seed(12)
+    x = torch.randn(M, C, generator=g, device="cuda")
+    y0 = ops.ln_mod(x).float()
+    y1 = ops.ln_mod(x + 3.0).float()                                                  # LayerNorm is shift invariant
+    assert float((y0 - y1).abs().max()) <= 0.0625 and float((y0 - y1).abs().mean()) <= 2e-3   # <= 2 bf16 ulps at |y| < 8
+    assert float((y0.mean(1)).abs().max()) <= 1e-2 and float((y0.pow(2).mean(1) - 1).abs().max()) <= 2e-2
+    q = torch.randn(M, C, generator=g, device="cuda").bfloat16()
+    w = torch.ones(C, device="cuda")
+    cos, sin = rope_tables((21, 30, 52), torch.device("cuda"))
+    plain = q.clone()
+    ops.rmsnorm_rope_(plain, w, None, None, 1e-6)
+    rot = q.clone()
+    ops.rmsnorm_rope_(rot, w, cos, sin, 1e-6, M, 0)
+    n0 = plain.float().view(M, C // 2, 2).norm(dim=2)
+    n1 = rot.float().view(M, C // 2, 2).norm(dim=2)
+    assert float((n0 - n1).abs().max()) <= 3e-2                                       # a rotation; bf16 output rounding only
+    assert not torch.equal(plain, rot)
+
+
+def test_scheduler_last_step_is_x0_full_latent():
+    from prfl_b200.scheduler import FlowUniPCMultistepScheduler
+    s = FlowUniPCMultistepScheduler(num_train_timesteps=1000, shift=1, use_dynamic_shifting=False)
+    s.set_timesteps(40, device="cuda", shift=5.0)
+    g = torch.Generator(device="cuda").manual_seed(13)
+    x = torch.randn(1, 16, 21, 90, 160, generator=g, device="cuda")                   # 720P x 81f latent
+    for t in s.timesteps:
+        v = torch.tanh(x) * 0.5
+        x = s.step(v, t, x, return_dict=False)[0]
+    assert torch.isfinite(x).all() and torch.equal(x, s.model_outputs[-1])

@@ -356,7 +356,7 @@ def test_adamw_step_and_sumsq(ops, n):
         acc = torch.zeros((), dtype=torch.float64, device="cuda")
         ops.sumsq_(grad, acc)
         want = grad.double().pow(2).sum()
-        assert abs(float(acc) - float(want)) <= 1e-9 * float(want)
+        assert abs(float(acc) - float(want)) <= 1e-6 * float(want)       # fp32 per-thread partials, double across CTAs
         coef = torch.clamp(1.0 / (acc.sqrt().float() + 1e-6), max=1.0)
         ref_p.grad = grad * coef
         opt.step()
