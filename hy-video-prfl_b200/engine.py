@@ -355,6 +355,52 @@ class BlockFn(torch.autograd.Function):
         return (dx, de, dctx, None, None, None, None, None, *pg)
 
 
+class HeadFn(torch.autograd.Function):
+    """Head of one sample (model.py:379-389: LayerNorm -> * (1 + e1) + e0 -> Linear(dim -> prod(patch) * out_dim), fp32 in the
+    reference) with fp32-grade products on the bf16 tensor pipe: h = hi + lo and W = Whi + Wlo are split into bf16 pairs and
+    hi Whi + hi Wlo + lo Whi is accumulated in fp32 (relative error ~1e-5); the same split gives the weight gradient
+    dW = dy^T h.  The input gradient goes through bf16 (dh = bf16(dy) W) into the LayerNorm backward kernel, as every other
+    activation gradient on the path does.  Backward recomputes the normalised activations instead of storing them."""
+
+    @staticmethod
+    def forward(ctx, x, shift, scale, weight, bias, head):
+        xf, sh, sc = (t.detach().float().contiguous() for t in (x, shift, scale))
+        w_hi, w_lo = head._split_operands()
+        hi, lo = ops.ln_mod_split(xf, sh, sc, head.eps)
+        o = ops.gemm(hi, w_hi, bias=bias.detach().float().contiguous(), epi=ops.EPI_F32)
+        ops.gemm(hi, w_lo, epi=ops.EPI_F32, out=o, beta=True)
+        ops.gemm(lo, w_hi, epi=ops.EPI_F32, out=o, beta=True)
+        ctx.save_for_backward(xf, sh, sc)
+        ctx.head = head
+        return o
+
+    @staticmethod
+    def backward(ctx, do):
+        xf, sh, sc = ctx.saved_tensors
+        head = ctx.head
+        need_x, need_sh, need_sc, need_w, need_b = ctx.needs_input_grad[:5]
+        do = do.float().contiguous()                                     # [L, 64] fp32
+        d_hi = ops.cast_bf16(do)
+        dW = db = dx = dsh = dsc = None
+        if need_w or need_b:
+            d_lo = ops.cast_bf16(do - d_hi.float())
+            if need_w:
+                hi, lo = ops.ln_mod_split(xf, sh, sc, head.eps)
+                dW = _wgrad(d_hi, hi)
+                ops.gemm(d_hi, lo, a_trans=True, b_trans=True, epi=ops.EPI_F32, out=dW, beta=True)
+                ops.gemm(d_lo, hi, a_trans=True, b_trans=True, epi=ops.EPI_F32, out=dW, beta=True)
+                del hi, lo
+            if need_b:
+                db = ops.colsum(d_hi) + ops.colsum(d_lo)
+        if need_x or need_sh or need_sc:
+            w_hi, _ = head._split_operands()
+            dh = ops.gemm(d_hi, w_hi, b_trans=True, epi=ops.EPI_BF16)    # [L, C] = dy . W   (W as the [K = 64, N = C] operand)
+            _, mean, rstd = ops.ln_mod(xf, sh, sc, eps=head.eps, save_stats=True)
+            dx = torch.zeros_like(xf)
+            dsh, dsc = ops.ln_mod_bwd(xf, dh, sc, None, mean, rstd, dx, need_sh or need_sc)
+        return dx, dsh, dsc, dW, db, None
+
+
 class LinearFn(torch.autograd.Function):
     """y = bf16(x W^T + b) through the tcgen05 GEMM, with dgrad / wgrad / bias-grad kernels in backward."""
 

@@ -377,9 +377,9 @@ class Head(nn.Module):
         assert e.dtype == torch.float32
         m = (self.modulation.float() + e.unsqueeze(1)).chunk(2, dim=1)                      # 2 x [B, 1, C]
         if torch.is_grad_enabled() and (x.requires_grad or e.requires_grad or self.head.weight.requires_grad):
-            # training: fp32 PyTorch ops (0.01 % of the step's FLOPs; a backward for the split kernels is not built yet)
-            h = F.layer_norm(x.float(), (self.dim,), None, None, self.eps) * (1 + m[1]) + m[0]
-            return F.linear(h, self.head.weight.float(), self.head.bias.float())
+            from .engine import HeadFn                                   # same kernels as below + their backward
+            return torch.stack([HeadFn.apply(x[i], m[0][i, 0], m[1][i, 0], self.head.weight, self.head.bias, self)
+                                for i in range(x.shape[0])])
         w_hi, w_lo = self._split_operands()
         bias = self.head.bias.detach().float().contiguous()
         outs = []
