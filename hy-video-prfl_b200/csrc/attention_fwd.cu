@@ -9,6 +9,13 @@
 // Warps: 0-7 softmax of Q tile 0, 8-15 softmax of Q tile 1 (two threads per row), 16 TMA producer, 17 MMA issuer.
 // TMEM: S0 [0,128) S1 [128,256) O0 [256,384) O1 [384,512); P_i (bf16) aliases columns [0,32) and [64,96) of S_i.
 // Roofline: tensor pipe, 4*Lq*Lk*128 flops per head.
+//
+// Wave quantisation.  A unit (one head x 256 queries over all keys) is one CTA and all units cost the same, so a grid of
+// U units on 148 SMs takes ceil(U / 148) waves: 640 units (L = 32 760, 5 heads per rank at 8 GPUs) run 5 waves with the
+// last one 32 % full.  When the remainder is at most half a wave, the launcher runs the full waves as usual and the
+// remaining units as a second launch split S = 2..4 ways along the KEY axis (flash-decoding style): each piece writes its
+// normalised fp32 partial output and log2-domain LSE to a caller-provided workspace and `attn_combine_kernel` merges
+// them (and performs the peer stores of the fused Ulysses epilogue).  640 units: 4 waves + 1/3 wave instead of 5.
 #include <math.h>
 
 #include <stdlib.h>
@@ -37,6 +44,12 @@ struct AttnFwdParams {
   // rank's [L_loc, H_total, 128] buffer over NVLink (peer-mapped pointers), at head head_off + h.  n_peer == 0: off.
   __nv_bfloat16* o_peer[8];
   int n_peer, L_loc, head_off;
+  // unit addressing + key-axis split (see "Wave quantisation" above)
+  int nq;            // 256-query blocks per head
+  int unit0;         // first unit of this launch; unit = unit0 + blockIdx.x = head * nq + q block
+  int n_split;       // pieces per unit along the key axis (blockIdx.y); 1 = write the final output directly
+  float* part_o;     // [blockIdx.x][n_split][256][128] fp32, normalised partial outputs
+  float* part_lse;   // [blockIdx.x][n_split][256]      log2-domain LSE of each partial
 };
 
 // FMA_MASK: which of the 8 (i = 0, 4, ..., 28) second pairs of each 32-column chunk take the FMA-pipe exp2 (bit i/4):
@@ -63,9 +76,13 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 14);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int head = blockIdx.y;
-  const int q0 = blockIdx.x * (2 * QT);
-  const int n_kv = (p.Lk + KT - 1) / KT;
+  const int unit = p.unit0 + blockIdx.x;
+  const int head = unit / p.nq;
+  const int q0 = (unit % p.nq) * (2 * QT);
+  const int n_kv_all = (p.Lk + KT - 1) / KT;
+  const int kv_per = (n_kv_all + p.n_split - 1) / p.n_split;
+  const int kv0 = blockIdx.y * kv_per;                         // first KV tile of this piece
+  const int n_kv = min(kv_per, n_kv_all - kv0);                // >= 1 (the launcher keeps n_split <= n_kv_all / 2)
 
   if (warp == AW_TMA && lane == 0) {
     tma_prefetch_desc(&tmQ);
@@ -103,11 +120,11 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         mbar_wait(&kempty[s], ph ^ 1);
         mbar_arrive_expect_tx(&kfull[s], TILE_BYTES);
 #pragma unroll
-        for (int c = 0; c < 2; ++c) tma_load_3d(sK + s * TILE_BYTES + c * 16384, &tmK, &kfull[s], c * 64, j * KT, head);
+        for (int c = 0; c < 2; ++c) tma_load_3d(sK + s * TILE_BYTES + c * 16384, &tmK, &kfull[s], c * 64, (kv0 + j) * KT, head);
         mbar_wait(&vempty[s], ph ^ 1);
         mbar_arrive_expect_tx(&vfull[s], TILE_BYTES);
 #pragma unroll
-        for (int c = 0; c < 2; ++c) tma_load_3d(sV + s * TILE_BYTES + c * 16384, &tmV, &vfull[s], c * 64, j * KT, head);
+        for (int c = 0; c < 2; ++c) tma_load_3d(sV + s * TILE_BYTES + c * 16384, &tmV, &vfull[s], c * 64, (kv0 + j) * KT, head);
       }
     }
   } else if (warp == AW_MMA) {
@@ -190,7 +207,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     for (int j = 0; j < n_kv; ++j) {
       mbar_wait(&sfull[t], j & 1);
       tc_fence_after();
-      const int valid = p.Lk - j * KT - half * 64;   // my columns >= valid are padding (only the last tile is ragged)
+      const int valid = p.Lk - (kv0 + j) * KT - half * 64;   // my columns >= valid are padding (only the last tile is ragged)
       uint32_t pk[32];                                // my 64 keys as packed bf16x2, stored only after the max check
       float tile_sum = 0.f, tile_max = -INFINITY;
       auto exp_pass = [&](const float m_ref) {
@@ -281,33 +298,51 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     tc_fence_after();
     const float inv_l = 1.0f / l_tot;
     const bool row_ok = row < p.Lq;
-    __nv_bfloat16* orow;
-    if (p.n_peer > 0) {
-      const int rk = row_ok ? row / p.L_loc : 0;
-      orow = p.o_peer[rk] + (int64_t)(row - rk * p.L_loc) * p.o_ld_tok + (int64_t)(p.head_off + head) * p.o_ld_head;
-    } else {
-      orow = p.o + (int64_t)row * p.o_ld_tok + (int64_t)head * p.o_ld_head;
-    }
-    orow += half * 64;
+    if (p.n_split > 1) {
+      // one piece of a key-split unit: normalised fp32 partial + its LSE (log2 domain) for attn_combine_kernel
+      const int64_t prow = ((int64_t)blockIdx.x * p.n_split + blockIdx.y) * (2 * QT) + t * QT + r;
+      float* dst = p.part_o + prow * HD + half * 64;
 #pragma unroll 1
-    for (int c = 0; c < 2; ++c) {
-      uint32_t o[32];
-      tmem_ld32(o_addr + c * 32, o);
-      tmem_wait_ld();
-      if (row_ok) {
+      for (int c = 0; c < 2; ++c) {
+        uint32_t o[32];
+        tmem_ld32(o_addr + c * 32, o);
+        tmem_wait_ld();
 #pragma unroll
-        for (int i = 0; i < 32; i += 8) {
-          uint4 v;
-          v.x = pack_bf16x2(__uint_as_float(o[i]) * inv_l, __uint_as_float(o[i + 1]) * inv_l);
-          v.y = pack_bf16x2(__uint_as_float(o[i + 2]) * inv_l, __uint_as_float(o[i + 3]) * inv_l);
-          v.z = pack_bf16x2(__uint_as_float(o[i + 4]) * inv_l, __uint_as_float(o[i + 5]) * inv_l);
-          v.w = pack_bf16x2(__uint_as_float(o[i + 6]) * inv_l, __uint_as_float(o[i + 7]) * inv_l);
-          *reinterpret_cast<uint4*>(orow + c * 32 + i) = v;
-        }
+        for (int i = 0; i < 32; i += 4)
+          *reinterpret_cast<float4*>(dst + c * 32 + i) = make_float4(__uint_as_float(o[i]) * inv_l, __uint_as_float(o[i + 1]) * inv_l,
+                                                                      __uint_as_float(o[i + 2]) * inv_l, __uint_as_float(o[i + 3]) * inv_l);
+        __syncwarp();
       }
-      __syncwarp();
+      if (half == 0) p.part_lse[prow] = m_used + log2f(l_tot);
+    } else {
+      __nv_bfloat16* orow;
+      if (p.n_peer > 0) {
+        const int rk = row_ok ? row / p.L_loc : 0;
+        orow = p.o_peer[rk] + (int64_t)(row - rk * p.L_loc) * p.o_ld_tok + (int64_t)(p.head_off + head) * p.o_ld_head;
+      } else {
+        orow = p.o + (int64_t)row * p.o_ld_tok + (int64_t)head * p.o_ld_head;
+      }
+      orow += half * 64;
+#pragma unroll 1
+      for (int c = 0; c < 2; ++c) {
+        uint32_t o[32];
+        tmem_ld32(o_addr + c * 32, o);
+        tmem_wait_ld();
+        if (row_ok) {
+#pragma unroll
+          for (int i = 0; i < 32; i += 8) {
+            uint4 v;
+            v.x = pack_bf16x2(__uint_as_float(o[i]) * inv_l, __uint_as_float(o[i + 1]) * inv_l);
+            v.y = pack_bf16x2(__uint_as_float(o[i + 2]) * inv_l, __uint_as_float(o[i + 3]) * inv_l);
+            v.z = pack_bf16x2(__uint_as_float(o[i + 4]) * inv_l, __uint_as_float(o[i + 5]) * inv_l);
+            v.w = pack_bf16x2(__uint_as_float(o[i + 6]) * inv_l, __uint_as_float(o[i + 7]) * inv_l);
+            *reinterpret_cast<uint4*>(orow + c * 32 + i) = v;
+          }
+        }
+        __syncwarp();
+      }
+      if (row_ok && half == 0 && p.lse) p.lse[(int64_t)head * p.Lq + row] = (m_used + log2f(l_tot)) * 0.6931471805599453f;
     }
-    if (row_ok && half == 0 && p.lse) p.lse[(int64_t)head * p.Lq + row] = (m_used + log2f(l_tot)) * 0.6931471805599453f;
   }
 
   tc_fence_before();
@@ -318,14 +353,87 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   }
 }
 
+// Merge the key-split pieces of the tail units: one warp per query row, lane = 4 output columns.
+//   w_s = 2^(lse_s - max lse), O = sum_s w_s O_s / sum_s w_s, LSE = (max + log2 sum_s w_s) ln 2
+__global__ void __launch_bounds__(256) attn_combine_kernel(const AttnFwdParams p, int n_units) {
+  const int lane = threadIdx.x & 31;
+  const int64_t w = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (w >= (int64_t)n_units * (2 * QT)) return;
+  const int ui = (int)(w / (2 * QT)), rr = (int)(w % (2 * QT));
+  const int unit = p.unit0 + ui;
+  const int head = unit / p.nq;
+  const int row = (unit % p.nq) * (2 * QT) + rr;
+  if (row >= p.Lq) return;
+  float m = -INFINITY;
+  for (int s = 0; s < p.n_split; ++s) m = fmaxf(m, p.part_lse[((int64_t)ui * p.n_split + s) * (2 * QT) + rr]);
+  float den = 0.f;
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int s = 0; s < p.n_split; ++s) {
+    const int64_t prow = ((int64_t)ui * p.n_split + s) * (2 * QT) + rr;
+    const float ws = fast_exp2(p.part_lse[prow] - m);
+    const float4 v = *reinterpret_cast<const float4*>(p.part_o + prow * HD + lane * 4);
+    den += ws;
+    acc.x += ws * v.x; acc.y += ws * v.y; acc.z += ws * v.z; acc.w += ws * v.w;
+  }
+  const float inv = 1.0f / den;
+  __nv_bfloat16* orow;
+  if (p.n_peer > 0) {
+    const int rk = row / p.L_loc;
+    orow = p.o_peer[rk] + (int64_t)(row - rk * p.L_loc) * p.o_ld_tok + (int64_t)(p.head_off + head) * p.o_ld_head;
+  } else {
+    orow = p.o + (int64_t)row * p.o_ld_tok + (int64_t)head * p.o_ld_head;
+  }
+  uint2 o;
+  o.x = pack_bf16x2(acc.x * inv, acc.y * inv);
+  o.y = pack_bf16x2(acc.z * inv, acc.w * inv);
+  *reinterpret_cast<uint2*>(orow + lane * 4) = o;
+  if (lane == 0 && p.lse) p.lse[(int64_t)head * p.Lq + row] = (m + log2f(den)) * 0.6931471805599453f;
+}
+
 }  // namespace prfl
 
 using namespace prfl;
 
+// Tail plan: units beyond the last full wave are split `n_split` ways along the key axis when that shortens the kernel.
+struct SplitPlan {
+  int n_units, n_main, n_tail, n_split;
+};
+static SplitPlan plan_split(int Lq, int Lk, int H) {
+  SplitPlan sp;
+  const int nq = (Lq + 2 * QT - 1) / (2 * QT);
+  sp.n_units = nq * H;
+  sp.n_main = sp.n_units;
+  sp.n_tail = 0;
+  sp.n_split = 1;
+  static const int force = [] { const char* e = getenv("PRFL_ATTN_SPLIT"); return e ? atoi(e) : -1; }();   // 0: off, 2..4: always
+  const int sms = sm_count();
+  const int n_kv = (Lk + KT - 1) / KT;
+  if (force == 0 || sms <= 0) return sp;
+  int rem = sp.n_units % sms, s = 1;
+  if (force >= 2) {
+    s = force;
+    if (rem == 0) rem = sp.n_units < sms ? sp.n_units : sms;
+  } else if (sp.n_units > sms && rem > 0 && 2 * rem <= sms && n_kv >= 32) {
+    s = sms / rem;
+    if (s > 4) s = 4;
+  }
+  while (s >= 2 && (s - 1) * ((n_kv + s - 1) / s) >= n_kv) --s;     // every piece must own at least one KV tile
+  if (s < 2 || n_kv < 2 * s) return sp;
+  sp.n_tail = rem;
+  sp.n_main = sp.n_units - rem;
+  sp.n_split = s;
+  return sp;
+}
+
+extern "C" int64_t prfl_attn_fwd_ws_bytes(int Lq, int Lk, int H) {
+  const SplitPlan sp = plan_split(Lq, Lk, H);
+  return sp.n_tail == 0 ? 0 : (int64_t)sp.n_tail * sp.n_split * (2 * QT) * (HD + 1) * (int64_t)sizeof(float);
+}
+
 static int attn_fwd_launch(const void* q, int64_t q_ld_tok, int64_t q_ld_head, const void* k, int64_t k_ld_tok, int64_t k_ld_head,
                            const void* v, int64_t v_ld_tok, int64_t v_ld_head, void* o, int64_t o_ld_tok, int64_t o_ld_head,
                            float* lse, int Lq, int Lk, int H, float scale, void* const* o_peers, int n_peer, int L_loc,
-                           int head_off, prfl_stream_t stream) {
+                           int head_off, void* ws, prfl_stream_t stream) {
   PRFL_CHECK_ARCH();
   PRFL_REQUIRE(Lq > 0 && Lk > 0 && H > 0, PRFL_E_SHAPE, "attn_fwd: Lq=%d Lk=%d H=%d", Lq, Lk, H);
   PRFL_REQUIRE(q_ld_tok % 8 == 0 && q_ld_head % 8 == 0 && k_ld_tok % 8 == 0 && k_ld_head % 8 == 0 && v_ld_tok % 8 == 0 &&
@@ -353,25 +461,49 @@ static int attn_fwd_launch(const void* q, int64_t q_ld_tok, int64_t q_ld_head, c
   p.scale_log2 = scale * 1.4426950408889634f;
   p.n_peer = n_peer; p.L_loc = L_loc; p.head_off = head_off;
   for (int i = 0; i < 8; ++i) p.o_peer[i] = i < n_peer ? (__nv_bfloat16*)o_peers[i] : nullptr;
-  dim3 grid((Lq + 2 * QT - 1) / (2 * QT), H);
-  kern<<<grid, ATT_THREADS, ATT_SMEM, (cudaStream_t)stream>>>(tmQ, tmK, tmV, p);
-  count_launch();
-  PRFL_LAUNCH_CHECK("attn_fwd");
+  SplitPlan sp = plan_split(Lq, Lk, H);
+  if (ws == nullptr) {                      // no workspace from the caller: one launch over all units
+    sp.n_main = sp.n_units;
+    sp.n_tail = 0;
+  }
+  PRFL_REQUIRE((reinterpret_cast<uintptr_t>(ws) & 15) == 0, PRFL_E_ALIGN, "attn_fwd: workspace must be 16-byte aligned");
+  p.nq = (Lq + 2 * QT - 1) / (2 * QT);
+  p.unit0 = 0;
+  p.n_split = 1;
+  p.part_o = p.part_lse = nullptr;
+  if (sp.n_main > 0) {
+    kern<<<dim3(sp.n_main, 1), ATT_THREADS, ATT_SMEM, (cudaStream_t)stream>>>(tmQ, tmK, tmV, p);
+    count_launch();
+    PRFL_LAUNCH_CHECK("attn_fwd");
+  }
+  if (sp.n_tail > 0) {
+    p.unit0 = sp.n_main;
+    p.n_split = sp.n_split;
+    p.part_o = static_cast<float*>(ws);
+    p.part_lse = p.part_o + (int64_t)sp.n_tail * sp.n_split * (2 * QT) * HD;
+    kern<<<dim3(sp.n_tail, sp.n_split), ATT_THREADS, ATT_SMEM, (cudaStream_t)stream>>>(tmQ, tmK, tmV, p);
+    count_launch();
+    PRFL_LAUNCH_CHECK("attn_fwd (key-split tail)");
+    const int64_t rows = (int64_t)sp.n_tail * (2 * QT);
+    attn_combine_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, (cudaStream_t)stream>>>(p, sp.n_tail);
+    count_launch();
+    PRFL_LAUNCH_CHECK("attn_combine");
+  }
   return PRFL_OK;
 }
 
 extern "C" int prfl_attn_fwd(const void* q, int64_t q_ld_tok, int64_t q_ld_head, const void* k, int64_t k_ld_tok,
                              int64_t k_ld_head, const void* v, int64_t v_ld_tok, int64_t v_ld_head, void* o, int64_t o_ld_tok,
-                             int64_t o_ld_head, float* lse, int Lq, int Lk, int H, float scale, prfl_stream_t stream) {
+                             int64_t o_ld_head, float* lse, int Lq, int Lk, int H, float scale, void* ws, prfl_stream_t stream) {
   return attn_fwd_launch(q, q_ld_tok, q_ld_head, k, k_ld_tok, k_ld_head, v, v_ld_tok, v_ld_head, o, o_ld_tok, o_ld_head, lse, Lq, Lk,
-                         H, scale, nullptr, 0, 0, 0, stream);
+                         H, scale, nullptr, 0, 0, 0, ws, stream);
 }
 
 extern "C" int prfl_attn_fwd_p2p(const void* q, int64_t q_ld_tok, int64_t q_ld_head, const void* k, int64_t k_ld_tok,
                                  int64_t k_ld_head, const void* v, int64_t v_ld_tok, int64_t v_ld_head, void* const* o_peers,
                                  int n_peer, int L_loc, int head_off, int64_t o_ld_tok, int64_t o_ld_head, float* lse, int Lq,
-                                 int Lk, int H, float scale, prfl_stream_t stream) {
+                                 int Lk, int H, float scale, void* ws, prfl_stream_t stream) {
   PRFL_REQUIRE(n_peer >= 1 && o_peers, PRFL_E_SHAPE, "attn_fwd_p2p: needs peer pointers");
   return attn_fwd_launch(q, q_ld_tok, q_ld_head, k, k_ld_tok, k_ld_head, v, v_ld_tok, v_ld_head, o_peers[0], o_ld_tok, o_ld_head, lse,
-                         Lq, Lk, H, scale, o_peers, n_peer, L_loc, head_off, stream);
+                         Lq, Lk, H, scale, o_peers, n_peer, L_loc, head_off, ws, stream);
 }

@@ -148,6 +148,12 @@ def gemm(a: torch.Tensor, b: torch.Tensor, *, a_trans: bool = False, b_trans: bo
     return out
 
 
+def _attn_ws(Lq: int, Lk: int, H: int, device):
+    """Workspace for the key-split tail of the forward kernel (wave quantisation, csrc/attention_fwd.cu); None if unused."""
+    n = int(lib().prfl_attn_fwd_ws_bytes(Lq, Lk, H))
+    return torch.empty(n // 4, dtype=f32, device=device) if n > 0 else None
+
+
 def attn_fwd(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, scale: Optional[float] = None,
              out: Optional[torch.Tensor] = None, need_lse: bool = False):
     """q: [Lq, H, 128], k/v: [Lk, H, 128] bf16 views (last stride 1; token / head strides free)."""
@@ -162,9 +168,11 @@ def attn_fwd(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, scale: Optional[
     lse = torch.empty(H, Lq, dtype=f32, device=q.device) if need_lse else None
     if scale is None:
         scale = 1.0 / math.sqrt(128)
+    ws = _attn_ws(Lq, Lk, H, q.device)
     with _timed("attn_fwd_self" if Lk > 1024 else "attn_fwd_cross"):
         check(lib().prfl_attn_fwd(_p(q), q.stride(0), q.stride(1), _p(k), k.stride(0), k.stride(1), _p(v), v.stride(0), v.stride(1),
-                                  _p(out), out.stride(0), out.stride(1), _p(lse), Lq, Lk, H, float(scale), _stream()), "prfl_attn_fwd")
+                                  _p(out), out.stride(0), out.stride(1), _p(lse), Lq, Lk, H, float(scale), _p(ws), _stream()),
+              "prfl_attn_fwd")
     return (out, lse) if need_lse else out
 
 
@@ -276,10 +284,11 @@ def attn_fwd_p2p(q, k, v, o_peer_ptrs, L_loc: int, head_off: int, H_total: int, 
     Lk = k.shape[0]
     if scale is None:
         scale = 1.0 / math.sqrt(128)
+    ws = _attn_ws(Lq, Lk, H, q.device)
     with _timed("attn_fwd_self" if Lk > 1024 else "attn_fwd_cross"):
         check(lib().prfl_attn_fwd_p2p(_p(q), q.stride(0), q.stride(1), _p(k), k.stride(0), k.stride(1), _p(v), v.stride(0), v.stride(1),
                                       _ptr_array(o_peer_ptrs), len(o_peer_ptrs), L_loc, head_off, H_total * 128, 128, None, Lq, Lk, H,
-                                      float(scale), _stream()), "prfl_attn_fwd_p2p")
+                                      float(scale), _p(ws), _stream()), "prfl_attn_fwd_p2p")
 
 
 def cast_bf16(src: torch.Tensor) -> torch.Tensor:

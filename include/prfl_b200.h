@@ -128,10 +128,15 @@ int prfl_gemm_bf16(const void* A, int64_t lda, int a_trans, const void* B, int64
  *   O[i,h,:] = softmax_j(scale * Q[i,h,:] . K[j,h,:]) V[j,h,:],  j < Lk
  * q/k/v/o: bf16, element (token t, head h, dim d) at base + t*ld_tok + h*ld_head + d (strides in
  * elements, multiples of 8: lets them alias a fused QKV buffer or an Ulysses staging layout).
- * lse: [H, Lq] f32 (natural-log sum-exp of the scaled scores) or NULL; needed by the backward. */
+ * lse: [H, Lq] f32 (natural-log sum-exp of the scaled scores) or NULL; needed by the backward.
+ * ws: NULL, or a 16-byte aligned device workspace of prfl_attn_fwd_ws_bytes(Lq, Lk, H) bytes.  With a workspace the
+ * units past the last full wave of CTAs are split along the key axis and merged by a second kernel (wave quantisation:
+ * 640 equal units on 148 SMs would otherwise run 5 waves, the last 32 % full); results differ from the unsplit launch by
+ * fp32 summation order only. */
+int64_t prfl_attn_fwd_ws_bytes(int Lq, int Lk, int H);
 int prfl_attn_fwd(const void* q, int64_t q_ld_tok, int64_t q_ld_head, const void* k, int64_t k_ld_tok,
                   int64_t k_ld_head, const void* v, int64_t v_ld_tok, int64_t v_ld_head, void* o, int64_t o_ld_tok,
-                  int64_t o_ld_head, float* lse, int Lq, int Lk, int H, float scale, prfl_stream_t stream);
+                  int64_t o_ld_head, float* lse, int Lq, int Lk, int H, float scale, void* ws, prfl_stream_t stream);
 /* Same kernel with the Ulysses output exchange (model.py:195-196, communication.py:91-123) fused into its epilogue:
  * this rank computed H = H_total/P heads over all Lq tokens; row i is stored directly into rank (i / L_loc)'s
  * [L_loc, H_total, 128] buffer o_peers[i / L_loc] (peer-mapped NVLink pointer; HOST array of n_peer device pointers) at
@@ -139,7 +144,7 @@ int prfl_attn_fwd(const void* q, int64_t q_ld_tok, int64_t q_ld_head, const void
 int prfl_attn_fwd_p2p(const void* q, int64_t q_ld_tok, int64_t q_ld_head, const void* k, int64_t k_ld_tok,
                       int64_t k_ld_head, const void* v, int64_t v_ld_tok, int64_t v_ld_head, void* const* o_peers,
                       int n_peer, int L_loc, int head_off, int64_t o_ld_tok, int64_t o_ld_head, float* lse, int Lq, int Lk,
-                      int H, float scale, prfl_stream_t stream);
+                      int H, float scale, void* ws, prfl_stream_t stream);
 /* Backward (replaces flash_attn's bwd kernels reached through autograd from the same call sites): dq, dk, dv (bf16,
  * same addressing as q/k/v) from q, k, v, o, dout and the forward's lse.  ws: f32 workspace of
  * prfl_attn_bwd_ws_floats(Lq, H) elements (16-byte aligned), filled here with -lse*log2(e) and -rowsum(dout * o) padded

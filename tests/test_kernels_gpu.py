@@ -148,6 +148,27 @@ def test_attn_fwd(ops, Lq, Lk, H):
     torch.testing.assert_close(lse, lse_ref, rtol=1e-3, atol=2e-3)
 
 
+@pytest.mark.parametrize("Lq,Lk,H", [(4096, 4096, 10), (4000, 4100, 10), (2100, 8200, 17)])
+def test_attn_fwd_key_split_tail(ops, Lq, Lk, H):
+    """Shapes whose unit count leaves a small remainder modulo the SM count (160 / 153 units on 148 SMs): the tail units run
+    split along the key axis + combine (csrc/attention_fwd.cu, "Wave quantisation").  Same tolerance as the plain kernel."""
+    from prfl_b200 import _lib
+    assert _lib.lib().prfl_attn_fwd_ws_bytes(Lq, Lk, H) > 0, "this shape is meant to take the split path"
+    q = _rand(Lq, H, 128, dtype=torch.bfloat16, seed=40)
+    k = _rand(Lk, H, 128, dtype=torch.bfloat16, seed=41)
+    v = _rand(Lk, H, 128, dtype=torch.bfloat16, seed=42)
+    out, lse = ops.attn_fwd(q, k, v, need_lse=True)
+    ref, lse_ref = _attn_ref(q, k, v, 1 / math.sqrt(128))
+    for h0 in range(0, H, 4):                               # tail units are the LAST heads: check every head group
+        cos, rel = cos_rel(out[:, h0:h0 + 4], ref[:, h0:h0 + 4])
+        assert cos > 0.9999 and rel < 2e-2, (h0, cos, rel)
+    torch.testing.assert_close(lse, lse_ref, rtol=1e-3, atol=2e-3)
+    # gradients through the split forward's LSE / O
+    do = _rand(Lq, H, 128, dtype=torch.bfloat16, seed=43)
+    dq, dk, dv = ops.attn_bwd(q, k, v, out, do, lse)
+    assert torch.isfinite(dq.float()).all() and torch.isfinite(dk.float()).all() and torch.isfinite(dv.float()).all()
+
+
 def test_attn_fwd_strided_and_peaked(ops):
     """q/k/v as slices of one fused [L, 3, H, 128] buffer; large-magnitude scores exercise the lazy rescale."""
     L, H = 700, 2
