@@ -514,10 +514,12 @@ class WanModel(nn.Module):
         return ctx
 
     def forward(self, x, t, context, seq_len, clip_fea=None, y=None, cond_flag=False, output_features=False,
-                selected_layers=[20, 30, 40]):
+                selected_layers=[20, 30, 40], gather_features=True):
         """Same contract as the reference (model.py:534-681): x list of [C_in, F, H, W], t [B], context list of
         [L, C]; returns a list of [C_out, F, H, W] fp32 tensors, or with output_features the list of
-        [B, L, dim] fp32 features after the selected (1-based) blocks."""
+        [B, L, dim] fp32 features after the selected (1-based) blocks.  `gather_features=False` (extension, sequence
+        parallelism only) returns each rank's own [B, L/P, dim] token chunk instead of all-gathering it (for
+        `QueryAttention(..., sp_local=True)`)."""
         prepared = context if isinstance(context, PreparedContext) else None
         if self.model_type in ("i2v", "flf2v"):
             assert (clip_fea is not None or prepared is not None) and y is not None
@@ -570,7 +572,7 @@ class WanModel(nn.Module):
             finally:
                 block.cross_attn.__dict__.pop("_kv_cache", None)
             if output_features and index + 1 in selected_layers:
-                if get_sequence_parallel_state():
+                if get_sequence_parallel_state() and gather_features:
                     features_list.append(all_gather(xs, dim=1))
                 else:
                     features_list.append(xs if xs.requires_grad else xs.clone())

@@ -39,6 +39,30 @@ class _SqPool(torch.autograd.Function):
         return (dx if ctx.needs_input_grad[0] else None), dwk
 
 
+def _sp_pool(x_local: torch.Tensor, wk_eff: torch.Tensor) -> torch.Tensor:
+    """Softmax pooling over the tokens of ALL sequence-parallel ranks from per-rank partial poolings:
+    pooled = sum_r w_r pooled_r / sum_r w_r with w_r = sum_r * exp(max_r - max)."""
+    import torch.distributed as dist
+    from .parallel import get_sequence_parallel_state, nccl_info
+    pooled, _, stats = ops.sq_pool(x_local, wk_eff)                  # pooled [nh, C] (local softmax), stats [max | sum]
+    if not get_sequence_parallel_state():
+        return pooled
+    nh, C = pooled.shape
+    packed = torch.cat([pooled, stats.view(2, nh).t()], dim=1).contiguous()        # [nh, C + 2]
+    allp = torch.empty((nccl_info.sp_size,) + tuple(packed.shape), dtype=packed.dtype, device=packed.device)
+    dist.all_gather_into_tensor(allp.view(-1), packed.view(-1), group=nccl_info.group)
+    return merge_partial_poolings(allp)
+
+
+def merge_partial_poolings(allp: torch.Tensor) -> torch.Tensor:
+    """allp [P, nh, C + 2]: per rank the locally normalised pooling [nh, C], the local score max and the local sum of
+    exp(score - max).  Returns the pooling under the softmax over the union of all ranks' tokens, [nh, C]."""
+    C = allp.shape[2] - 2
+    mx, sm = allp[:, :, C], allp[:, :, C + 1]                        # [P, nh]
+    w = sm * torch.exp(mx - mx.max(dim=0, keepdim=True).values)
+    return (allp[:, :, :C] * w.unsqueeze(-1)).sum(0) / w.sum(0).unsqueeze(-1)
+
+
 class QueryAttention(nn.Module):
     """network.py:8-110."""
 
@@ -57,8 +81,12 @@ class QueryAttention(nn.Module):
         self.queries = nn.Parameter(torch.randn(num_queries, feature_dim))
         nn.init.xavier_uniform_(self.queries)
 
-    def forward(self, x, e=None, text=None):
-        """x: [B, L, C] or [n_sel, B, L, C] fp32 features (network.py:44-110)."""
+    def forward(self, x, e=None, text=None, sp_local: bool = False):
+        """x: [B, L, C] or [n_sel, B, L, C] fp32 features (network.py:44-110).
+        `sp_local=True` (no-grad scoring under Ulysses sequence parallelism): x holds only THIS rank's token chunk
+        [.., L/P, C]; every rank pools its chunk and the per-rank (max, sum, pooled) triples are merged exactly
+        (softmax over the union of the chunks) through one tiny all-gather — instead of all-gathering the fp32 features
+        (671 MB at 480P) and repeating the identical pooling on every rank as the reference does."""
         assert not (self.training and self.multihead_attn.dropout > 0), "dropout in the pooling is not supported"
         shape = x.shape
         if x.dim() == 2:
@@ -77,7 +105,11 @@ class QueryAttention(nn.Module):
         wv, bv = w[2 * C:].view(nh, hd, C), b[2 * C:]
         outs = []
         for i in range(bsz):
-            pooled = _SqPool.apply(x[i].float().contiguous(), wk_eff.contiguous())         # [nh, C]
+            if sp_local:
+                assert not torch.is_grad_enabled(), "sp_local pooling is the no-grad scoring path"
+                pooled = _sp_pool(x[i].float().contiguous(), wk_eff.contiguous())
+            else:
+                pooled = _SqPool.apply(x[i].float().contiguous(), wk_eff.contiguous())     # [nh, C]
             o = torch.einsum("hc,hdc->hd", pooled, wv).reshape(1, C) + bv
             outs.append(F.linear(o, mha.out_proj.weight.float(), mha.out_proj.bias.float()))
         out = torch.cat(outs)                                                              # [bsz, C]

@@ -3,6 +3,7 @@ truncated Wan-DiT (first `num_blocks` blocks, head removed) -> features after th
 QueryAttention pooling -> MLP -> reward logit.  This is the public call bench.py times."""
 from __future__ import annotations
 
+import os
 from typing import Dict, List, Optional
 
 import torch
@@ -35,13 +36,18 @@ class PavrmScorer(nn.Module):
         mlp.load_state_dict(sd_mlp, strict=True)
         return cls(m, qa, mlp, num_blocks).to(device).eval()
 
-    def features(self, x: List[torch.Tensor], t, context, seq_len, clip_fea=None, y=None):
+    def features(self, x: List[torch.Tensor], t, context, seq_len, clip_fea=None, y=None, gather: bool = True):
         feats = self.transformer(x=x, t=t, context=context, seq_len=seq_len, clip_fea=clip_fea, y=y,
-                                 output_features=True, selected_layers=[self.feature_layer])
+                                 output_features=True, selected_layers=[self.feature_layer], gather_features=gather)
         return torch.stack(feats)                                    # list2batch: [n_sel, B, L, C]
 
     @torch.no_grad()
     def score(self, x, t, context, seq_len, clip_fea=None, y=None, return_features: bool = False):
+        from .parallel import get_sequence_parallel_state
+        if get_sequence_parallel_state() and not return_features and os.environ.get("PRFL_SP_POOL", "local") != "gather":
+            # sequence parallel: pool each rank's token chunk and merge the partial softmax poolings (no feature all-gather)
+            feats = self.features(x, t, context, seq_len, clip_fea, y, gather=False)
+            return self.mlp(self.query_attention(feats, sp_local=True))
         feats = self.features(x, t, context, seq_len, clip_fea, y)
         logit = self.mlp(self.query_attention(feats))                # [B, 1, 1]
         return (logit, feats) if return_features else logit

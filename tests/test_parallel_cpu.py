@@ -55,3 +55,22 @@ def test_ulysses_gloo_world2_matches_reference():
         exp = torch.arange(r * n, (r + 1) * n, dtype=torch.float32).view(1, -1, 1, 1).expand_as(xg)
         assert torch.equal(xg, exp)
         assert torch.equal(t, torch.zeros(3))            # broadcast from the group's first rank
+
+
+def test_merge_partial_poolings_equals_global_softmax_pooling():
+    """QueryAttention(sp_local=True): softmax pooling over the union of P token chunks from per-chunk (pooled, max, sum)."""
+    import torch
+    from prfl_b200.network import merge_partial_poolings
+    g = torch.Generator().manual_seed(4)
+    P, Ll, nh, C = 4, 37, 8, 48
+    x = torch.randn(P * Ll, C, generator=g, dtype=torch.float64)
+    wk = torch.randn(nh, C, generator=g, dtype=torch.float64)
+    scores = x @ wk.t() * 3.0                                            # [L, nh], spread so the chunks' maxima differ
+    want = torch.softmax(scores, 0).t() @ x                               # [nh, C]
+    parts = []
+    for r in range(P):
+        s_r, x_r = scores[r * Ll:(r + 1) * Ll], x[r * Ll:(r + 1) * Ll]
+        m = s_r.max(0).values
+        e = torch.exp(s_r - m)
+        parts.append(torch.cat([(e / e.sum(0)).t() @ x_r, m[:, None], e.sum(0)[:, None]], dim=1))
+    torch.testing.assert_close(merge_partial_poolings(torch.stack(parts)), want, rtol=1e-12, atol=1e-12)

@@ -66,6 +66,18 @@ def main():
     c, r = cos_rel(feats[0].cpu(), rf[0])
     print(f"[rank {rank}] gathered features: cos={c:.6f} rel={r:.4f} shape={tuple(feats[0].shape)}")
     ok &= c >= 0.999 and r <= 2e-2 and feats[0].shape == rf[0].shape
+    # reward scoring: pooled per rank + merged (QueryAttention sp_local) vs the oracle chain and vs the gathered path
+    from prfl_b200.pavrm import PavrmScorer
+    qa_sd, mlp_sd = synth.make_reward_state_dicts(cfg.dim, 52)
+    scorer = PavrmScorer.from_state_dicts(cfg.kwargs(), sd, qa_sd, mlp_sd, num_blocks=2)
+    args = ([u.cuda() for u in inp["x"]], inp["t"].cuda(), [c.cuda() for c in inp["context"]], inp["seq_len"])
+    logit_sp = scorer.score(*args)
+    logit_g, _ = scorer.score(*args, return_features=True)
+    with torch.no_grad():
+        logit_o, _ = O.pavrm_reward(sd, cfg, qa_sd, mlp_sd, inp["x"], inp["t"], inp["context"], inp["seq_len"],
+                                    selected_layers=(2,), num_blocks=2)
+    print(f"[rank {rank}] reward logit: sp-local {float(logit_sp):.6f} gathered {float(logit_g):.6f} oracle {float(logit_o):.6f}")
+    ok &= abs(float(logit_sp) - float(logit_g)) <= 1e-5 and abs(float(logit_sp) - float(logit_o)) <= 1e-2
     t = torch.tensor([1.0 if ok else 0.0], device="cuda")
     dist.all_reduce(t, op=dist.ReduceOp.MIN)
     dist.barrier()
