@@ -557,6 +557,9 @@ class WanModel(nn.Module):
         e0 = F.linear(F.silu(e), tp.weight.float(), tp.bias.float()).unflatten(1, (6, self.dim))
 
         use_kv_cache = prepared is not None and not torch.is_grad_enabled()
+        if prepared is not None and torch.is_grad_enabled() and any(p.requires_grad for p in self.text_embedding.parameters()):
+            raise RuntimeError("a PreparedContext is detached from the text / CLIP embedding weights: use it for no-grad forwards "
+                               "only, or pass the raw context when those weights are being trained")
         ctx = prepared.embedded if prepared is not None else self._embed_context(context, clip_fea)
 
         if get_sequence_parallel_state():
