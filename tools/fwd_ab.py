@@ -5,6 +5,9 @@ import sys
 import torch
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from prfl_b200 import _lib  # noqa: E402
+if os.environ.get("PRFL_LIB"):                      # A/B against another build of the library
+    _lib.LIB_PATH = os.environ["PRFL_LIB"]
 from prfl_b200 import ops  # noqa: E402
 
 L = int(sys.argv[1]) if len(sys.argv) > 1 else 32760
@@ -22,4 +25,4 @@ for _ in range(iters):
 b.record()
 torch.cuda.synchronize()
 ms = a.elapsed_time(b) / iters
-print(f"exp_fma={os.environ.get('PRFL_ATTN_EXP_FMA', '25')}% L={L} H={H}: fwd {ms:.3f} ms = {4.0 * L * L * 128 * H / ms / 1e9:.0f} TFLOP/s")
+print(f"lib={os.path.basename(_lib.LIB_PATH)} L={L} H={H}: fwd {ms:.3f} ms = {4.0 * L * L * 128 * H / ms / 1e9:.0f} TFLOP/s")
