@@ -1,4 +1,4 @@
-"""torchrun --nproc-per-node P tools/sp_check.py : Ulysses sequence-parallel forward + backward on P GPUs against
+"""torchrun --nproc-per-node P tests/sp_check.py : Ulysses sequence-parallel forward + backward on P GPUs against
 the reference goldens (tiny_t2v / tiny_i2v / tiny_reward-sized models) — the same fixtures the 1-GPU tests use.
 Checks, on every rank: noise prediction, features; and that the SUM over SP ranks of the partial weight gradients
 equals the reference's SP=1 gradient."""
@@ -10,7 +10,7 @@ import torch.distributed as dist
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-sys.path.insert(0, os.path.join(ROOT, "tests"))
+sys.path.insert(0, os.path.join(ROOT, "tests"))     # test infrastructure: the only place besides bench.py / smoke() that imports oracle/
 from conftest import cos_rel, golden  # noqa: E402
 from oracle import synth  # noqa: E402
 from oracle import wan_oracle as O  # noqa: E402
