@@ -6,6 +6,8 @@
 // CTA tile 128 x 256 x 64, UMMA 128x256x16, two 256-column accumulators in TMEM so the epilogue of tile i
 // overlaps the main loop of tile i+1.  Roofline: tensor pipe (2*M*N*K flops); smem operand traffic
 // 48 KB / 512 MMA cycles = 96 B/clk per SM, below the 128 B/clk shared-memory port.
+#include <atomic>
+
 #include "common.cuh"
 
 namespace prfl {
@@ -306,13 +308,13 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 
 template <bool A_T, bool B_T, int CG>
 static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, cudaStream_t st) {
-  static bool attr_set = false;
+  static std::atomic<bool> attr_set{false};     // forward and autograd threads may race here: the call is idempotent
   auto kern = gemm_bf16_kernel<A_T, B_T, CG>;
   constexpr int SMEM = GemmCfg<CG>::SMEM;
-  if (!attr_set) {
+  if (!attr_set.load(std::memory_order_acquire)) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
     if (e != cudaSuccess) return cuda_fail(e, "gemm: cudaFuncSetAttribute");
-    attr_set = true;
+    attr_set.store(true, std::memory_order_release);
   }
   const int total = p.tiles_m * p.tiles_n;          // tiles_m counts (128 * CG)-row tiles
   const int units = sm_count() / CG;
