@@ -36,5 +36,6 @@ for e in prof.key_averages():
     if "attn" in e.key:
         t = e.device_time_total / e.count / 1e3
         nm = e.key[:70]
-        hw = (8.0 if "Lb1" in e.key or "true" in e.key else 6.0) * L * L * 128 * H if "bwd" in e.key else 0
+        # hardware flops: dK/dV kernel (attn_bwd_kernel<true, ...>) runs 4 tile-GEMMs per tile pair, dQ (<false, ...>) 3
+        hw = (8.0 if "attn_bwd_kernel<true" in e.key else 6.0) * L * L * 128 * H if "bwd" in e.key else 0
         print(f"  {nm:70s} {t:8.3f} ms" + (f"  hardware {hw / t / 1e9:.0f} TFLOP/s" if hw else ""))
