@@ -400,15 +400,13 @@ using namespace prfl;
 struct SplitPlan {
   int n_units, n_main, n_tail, n_split;
 };
-static SplitPlan plan_split(int Lq, int Lk, int H) {
+static SplitPlan plan_split_for(int Lq, int Lk, int H, int sms, int force) {
   SplitPlan sp;
   const int nq = (Lq + 2 * QT - 1) / (2 * QT);
   sp.n_units = nq * H;
   sp.n_main = sp.n_units;
   sp.n_tail = 0;
   sp.n_split = 1;
-  static const int force = [] { const char* e = getenv("PRFL_ATTN_SPLIT"); return e ? atoi(e) : -1; }();   // 0: off, 2..4: always
-  const int sms = sm_count();
   const int n_kv = (Lk + KT - 1) / KT;
   if (force == 0 || sms <= 0) return sp;
   int rem = sp.n_units % sms, s = 1;
@@ -425,6 +423,16 @@ static SplitPlan plan_split(int Lq, int Lk, int H) {
   sp.n_main = sp.n_units - rem;
   sp.n_split = s;
   return sp;
+}
+static SplitPlan plan_split(int Lq, int Lk, int H) {
+  static const int force = [] { const char* e = getenv("PRFL_ATTN_SPLIT"); return e ? atoi(e) : -1; }();   // 0: off, 2..4: always
+  return plan_split_for(Lq, Lk, H, sm_count(), force);
+}
+
+// The split policy as a pure host function (no device needed): out = {units, units in the plain launch, tail units, pieces}
+extern "C" void prfl_attn_fwd_split_plan(int Lq, int Lk, int H, int n_sms, int* out4) {
+  const SplitPlan sp = plan_split_for(Lq, Lk, H, n_sms, -1);
+  out4[0] = sp.n_units; out4[1] = sp.n_main; out4[2] = sp.n_tail; out4[3] = sp.n_split;
 }
 
 extern "C" int64_t prfl_attn_fwd_ws_bytes(int Lq, int Lk, int H) {

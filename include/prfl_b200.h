@@ -134,6 +134,9 @@ int prfl_gemm_bf16(const void* A, int64_t lda, int a_trans, const void* B, int64
  * 640 equal units on 148 SMs would otherwise run 5 waves, the last 32 % full); results differ from the unsplit launch by
  * fp32 summation order only. */
 int64_t prfl_attn_fwd_ws_bytes(int Lq, int Lk, int H);
+/* The same policy as a pure host function (no device): out4 = {units, units of the plain launch, tail units, pieces per
+ * tail unit} for a GPU with n_sms SMs. */
+void prfl_attn_fwd_split_plan(int Lq, int Lk, int H, int n_sms, int* out4);
 int prfl_attn_fwd(const void* q, int64_t q_ld_tok, int64_t q_ld_head, const void* k, int64_t k_ld_tok,
                   int64_t k_ld_head, const void* v, int64_t v_ld_tok, int64_t v_ld_head, void* o, int64_t o_ld_tok,
                   int64_t o_ld_head, float* lse, int Lq, int Lk, int H, float scale, void* ws, prfl_stream_t stream);

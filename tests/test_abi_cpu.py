@@ -65,3 +65,29 @@ def test_rope_apply_free_function_matches_reference_golden():
     out = rope_apply(fx["rope_in"], torch.tensor([fx["rope_grid"]]), None)
     assert out.dtype == torch.float32
     torch.testing.assert_close(out, fx["rope_out"], rtol=1e-5, atol=1e-5)
+
+
+def test_attention_split_policy():
+    """Host logic of the forward attention's key-split tail (csrc/attention_fwd.cu, "Wave quantisation"), no device needed."""
+    from prfl_b200 import _lib
+
+    def plan(Lq, Lk, H, sms=148):
+        out = (ctypes.c_int * 4)()
+        _lib.lib().prfl_attn_fwd_split_plan(Lq, Lk, H, sms, out)
+        return tuple(out)
+
+    assert plan(32760, 32760, 5) == (640, 592, 48, 3)          # one rank's share at 8 GPUs: 4 waves + 48 units, split 3 ways
+    assert plan(32760, 32760, 20) == (2560, 2516, 44, 3)       # 2 GPUs
+    assert plan(32760, 32760, 40) == (5120, 5120, 0, 1)        # remainder 88 > half a wave: plain launch
+    assert plan(75600, 75600, 5) == (1480, 1480, 0, 1)         # 720P at 8 GPUs: exactly 10 waves
+    assert plan(4096, 512, 10)[2] == 0                          # cross-attention-sized key axis: never split
+    assert plan(300, 300, 2) == (4, 4, 0, 1)                    # fewer units than SMs
+    for Lq in (2100, 4096, 8200, 32760):
+        for Lk in (4096, 4100, 8200, 32760):
+            for H in (1, 3, 5, 10, 17, 40):
+                units, main, tail, pieces = plan(Lq, Lk, H)
+                n_kv = -(-Lk // 128)
+                assert units == main + tail and main % 148 == 0 or tail == 0
+                if tail:
+                    per = -(-n_kv // pieces)
+                    assert 2 <= pieces <= 4 and 2 * tail <= 148 and (pieces - 1) * per < n_kv      # no empty piece
