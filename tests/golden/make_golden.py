@@ -215,6 +215,18 @@ def case_unipc(name):
         loss.backward()
         grads[m] = dict(prev=prev.detach().clone(), loss=loss.detach().clone(), grad_w=wg.grad.clone(), grad_x=xg.grad.clone())
     fx["prfl"] = grads
+    # add_noise (fm_solvers_unipc.py:758-797): by timestep lookup, with a begin index, and after a step
+    sch = S.FlowUniPCMultistepScheduler(num_train_timesteps=1000, shift=1, use_dynamic_shifting=False)
+    sch.set_timesteps(40, device="cpu", shift=3.0)
+    clean = torch.randn((3,) + shape[1:], generator=g)
+    eps = torch.randn((3,) + shape[1:], generator=g)
+    ts = sch.timesteps[[0, 17, 39]]
+    an = {"by_timestep": sch.add_noise(clean, eps, ts).clone()}
+    sch.set_begin_index(5)
+    an["begin_index"] = sch.add_noise(clean, eps, ts).clone()
+    sch.step(toy_velocity(x_init, sch.timesteps[5], w), sch.timesteps[5], x_init)
+    an["after_step"] = sch.add_noise(clean, eps, ts).clone()
+    fx["add_noise"] = an
     torch.save(fx, os.path.join(HERE, name + ".pt"))
     print(name, "ok", {k: float(v["loss"]) for k, v in grads.items()})
 

@@ -141,3 +141,24 @@ def test_step_has_no_cpu_fallback():
     s.set_timesteps(4, device="cpu", shift=3.0)
     with pytest.raises(_lib.PrflError):
         s.step(torch.zeros(1, 4), s.timesteps[0], torch.zeros(1, 4))
+
+
+def test_add_noise_matches_reference():
+    """fm_solvers_unipc.py:758-797 (cold path, plain torch ops: runs on CPU): index by timestep / begin index / step index."""
+    from prfl_b200.scheduler import FlowUniPCMultistepScheduler
+    fx = golden("unipc")
+    g = torch.Generator().manual_seed(fx["seed"])
+    shape = fx["shape"]
+    torch.randn(shape, generator=g)
+    torch.randn(shape, generator=g)                          # x_init, w: advance the generator as the fixture did
+    clean = torch.randn((3,) + tuple(shape[1:]), generator=g)
+    eps = torch.randn((3,) + tuple(shape[1:]), generator=g)
+    s = FlowUniPCMultistepScheduler(num_train_timesteps=1000, shift=1, use_dynamic_shifting=False)
+    s.set_timesteps(40, device="cpu", shift=3.0)
+    ts = s.timesteps[[0, 17, 39]]
+    torch.testing.assert_close(s.add_noise(clean, eps, ts), fx["add_noise"]["by_timestep"], rtol=0, atol=0)
+    s.set_begin_index(5)
+    torch.testing.assert_close(s.add_noise(clean, eps, ts), fx["add_noise"]["begin_index"], rtol=0, atol=0)
+    s._step_index = 6                                        # the state after one step from begin index 5
+    torch.testing.assert_close(s.add_noise(clean, eps, ts), fx["add_noise"]["after_step"], rtol=0, atol=0)
+    assert len(s) == 1000 and s.scale_model_input(clean) is clean
