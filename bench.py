@@ -257,8 +257,9 @@ def run_ours(args):
             "roofline": {"kernel": "attn_fwd_kernel (self-attention fwd, tcgen05)", "bound": "tensor", "achieved": achieved,
                          "peak": pk["tf_sust"], "unit": "TFLOP/s", "frac": achieved / pk["tf_sust"],
                          # DRAM bytes per launch from the committed `ncu --set full` capture of this kernel at this shape
-                         # (profiles/r01_ncu_full_attn_gemm.csv: 1.031 GB read + 0.322 GB written; algorithmic Q,K,V,O = 1.342 GB)
-                         "traffic": 1.353e9 if world == 1 else None,
+                         # (profiles/r01_ncu_full_v2.csv: 1.049 GB read + 0.462 GB written; algorithmic Q,K,V,O = 1.342 GB;
+                         # the first capture of the round, r01_ncu_full_attn_gemm.csv, read 1.031 + 0.322 GB)
+                         "traffic": 1.511e9 if world == 1 else None,
                          "peak_source": pk["src"] + " sustained bf16", "launch_ms": attn_avg, "launches_timed": len(attn_ms),
                          "share_of_step": attn_avg * len(attn_ms) / max(ms, 1e-9)},
             "step_tflops": (8 * 41.96e12 + 3.4e12 * 0) / world / (per_step * 1e-3) / 1e12,
