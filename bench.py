@@ -1,19 +1,34 @@
 #!/usr/bin/env python
-"""bench.py — the hot path of HY-Video-PRFL on B200: PAVRM latent reward scoring with the Wan2.1-14B
-architecture (BASELINE.json configs[1]; the largest single-GPU configuration of the north-star path).
+"""bench.py — the hot path of HY-Video-PRFL on B200.
 
-A "step" = one scoring pass: patchify -> 8 Wan-DiT blocks (14B dims) over L = 32 760 video tokens
-(480P x 81 frames) -> single-query reward attention -> MLP -> reward logit.
-  value : DiT tokens/s (L x forwards / time) with the inputs already resident in HBM
-  e2e   : the same through the public call with HOST (pinned) inputs: H2D copy of latents / text states / t
-          and D2H read of the logit inside the timed region
-  roofline : the dominant kernel (self-attention forward, tcgen05): algorithmic 4*L^2*128*40 flops per launch
-             / its live CUDA-event duration, against the measured bf16 peak in MEASURED_PEAKS.json
-  cpu_baseline : the oracle port (torch CPU fp32) timed on this box's host cores on a bounded sample
-N > 1 (torchrun): the same sample, tokens sharded over N ranks with Ulysses sequence parallelism ("strong").
+Top-level line (same contract as round 1, so rounds compare): PAVRM latent reward scoring with the Wan2.1-14B
+architecture (BASELINE.json configs[1], the configuration labelled "1 B200").  A "step" = one scoring pass: patchify ->
+8 Wan-DiT blocks (14B dims) over L = 32 760 video tokens (480P x 81 frames) -> single-query reward attention -> MLP ->
+reward logit.
+  value    : DiT tokens/s (L x forwards / time) with the inputs already resident in HBM
+  e2e      : the same through the public call with HOST (pinned) inputs: H2D copy of latents / text states / t and D2H
+             read of the logit inside the timed region
+  roofline : the dominant kernel (self-attention forward, tcgen05): algorithmic 4*L^2*128*heads flops per launch / its
+             live CUDA-event duration, against the measured sustained bf16 peak in MEASURED_PEAKS.json; `traffic` is read
+             from the committed `ncu --set full` capture under profiles/
+  parity   : driver-visible numerics (a) N = 1: the SAME weights on the CPU oracle (fp32) and on the GPU, 14B dims
+             (5120 / 40 heads / ffn 13 824), 8 blocks + reward head, on the bounded sample the CPU leg times:
+             features cos / max-rel, |d logit|; (b) N > 1: Ulysses forward, sum-over-ranks gradients through the NCCL
+             all-to-all path and ShardedAdamW vs dense AdamW (tests/sp_check.py) + the same-weights check of (a) under SP
+  prfl_step: the HEADLINE metric of BASELINE.json — "PRFL train s/step & DiT tokens/s, 14B 720P x 81f, 1/2/4/8 B200":
+             train_step_refl-shaped step (tools/prfl_step.py) at L = 75 600, I2V architecture, Ulysses SP over the N ranks,
+             sharded fp32 master / AdamW state, for m in {0, 2} no-grad denoising forwards; 40 blocks where the training
+             state fits (N >= 4), else the largest depth that fits, stated
+  cpu_baseline : the oracle port (torch CPU fp32) timed on this box's host cores on the bounded sample (+ the GPU's
+             throughput on that same sample, `gpu_same_sample`, for a like-for-like ratio)
+  gpu_baseline : the same oracle port run on THIS GPU with eager PyTorch kernels — bf16 `F.linear` (cuBLAS), flash-attn 2
+             (`flash_attn_func`), ATen norms / fp64 RoPE — i.e. the reference's own kernel stack on the
+             full 32 760-token workload; `speedup` = ours / eager
+N > 1 (torchrun): one sample, tokens sharded over N ranks with Ulysses sequence parallelism ("strong").
 `--impl reference` times the reference algorithm's CPU port (oracle/) instead — reported baseline.
 """
 import argparse
+import glob
 import json
 import os
 import subprocess
@@ -27,9 +42,17 @@ sys.path.insert(0, ROOT)
 import torch  # noqa: E402
 
 LATENT_480P = (21, 60, 104)      # 81 frames x 480 x 832 -> VAE latent; tokens = 21 * 30 * 52 = 32 760
+SAMPLE_LATENT = (3, 32, 52)      # bounded sample for the CPU legs / same-weights parity: 3 * 16 * 26 = 1 248 tokens (divisible by 8)
 NUM_BLOCKS = 8                   # lrm.trainable_blocks [0..7], feature_layer [8]
 HEADS, HD = 40, 128
 WORKLOAD = "PAVRM T2V 480Px81f reward scoring, Wan2.1-14B arch (dim 5120, ffn 13824, 40 heads), 8 blocks + reward head, L=32760, batch 1"
+
+
+def bench_config(world):
+    """Identical in both arms (`--impl ours` / `--impl reference`): the workload both are measured on."""
+    return {"workload": WORKLOAD, "parallelism": f"ulysses_sp{world}", "weights": "random init (seed 0)",
+            "l2": "per-step working set (5.6 GB bf16 weights + >2 GB activations) >> 126 MB L2; no explicit flush",
+            "bounded_sample": "CPU legs run the same architecture and depth on latent 16x3x32x52 -> 1248 tokens"}
 
 
 def peaks():
@@ -39,6 +62,25 @@ def peaks():
         return dict(hbm=d.get("hbm_gbs", 6650.0), tf_burst=d.get("bf16_tflops", 1590.0),
                     tf_sust=d.get("bf16_tflops_sustained", 1400.0), src="measured")
     return dict(hbm=6650.0, tf_burst=1590.0, tf_sust=1400.0, src="fallback")
+
+
+def traffic_from_profiles(kernel_prefix="attn_fwd_kernel"):
+    """DRAM bytes per launch (read + write) of the dominant kernel from the newest committed `ncu --set full` summary
+    (profiles/r*_ncu_full*.csv, written by tools/summarize_ncu.py): (bytes, file) or (None, None)."""
+    unit = {"byte": 1.0, "kbyte": 1e3, "mbyte": 1e6, "gbyte": 1e9, "tbyte": 1e12}
+    for path in sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_ncu_full*.csv")), key=os.path.getmtime, reverse=True):
+        try:
+            import csv
+            rows = [r for r in csv.reader(l for l in open(path) if not l.startswith("#"))]
+            hdr, units = rows[0], rows[1]
+            ir, iw = hdr.index("dram__bytes_read.sum"), hdr.index("dram__bytes_write.sum")
+            for r in rows[2:]:
+                if r and r[0].startswith(kernel_prefix):
+                    return (float(r[ir]) * unit[units[ir].lower()] + float(r[iw]) * unit[units[iw].lower()],
+                            os.path.relpath(path, ROOT))
+        except Exception:
+            continue
+    return None, None
 
 
 class ClockSampler:
@@ -76,41 +118,38 @@ class ClockSampler:
 
 
 # ---------------------------------------------------------------------------------------------------
-def cpu_sample(threads=None, blocks=NUM_BLOCKS, latent=(3, 30, 52), repeats=1):
-    """The oracle (CPU restatement of the reference path) on a bounded sample of the same workload:
-    14B architecture, `blocks` blocks + reward head, a short clip (latent 3x30x52 -> 1170 tokens)."""
+# CPU legs (the oracle: the only code below that touches oracle/)
+# ---------------------------------------------------------------------------------------------------
+def sample_inputs():
     from oracle import synth
+    cfg = synth.cfg_14b("t2v", layers=NUM_BLOCKS)
+    return cfg, synth.make_inputs(cfg, SAMPLE_LATENT, 2, text_tokens=512)
+
+
+def cpu_oracle_pass(sd, qa, mlp, threads=None, repeats=1):
+    """One PAVRM scoring pass of the oracle (CPU fp32) on the bounded sample with the given weights.
+    Returns (tokens, [seconds], logit, features)."""
     from oracle import wan_oracle as O
     if threads:
         torch.set_num_threads(threads)
-    cfg = synth.cfg_14b("t2v", layers=blocks)
-    g = torch.Generator().manual_seed(0)
-    sd, by_shape = {}, {}
-    for k, v in _shapes_14b(cfg).items():       # cheap init: values do not matter for timing, so tensors of one
-        if len(v) > 1:                            # shape share storage (reads still stream the full matrix per use)
-            if v not in by_shape:
-                by_shape[v] = torch.empty(v).uniform_(-0.02, 0.02, generator=g)
-            sd[k] = by_shape[v]
-        else:
-            sd[k] = torch.zeros(v)
-        if k.endswith("norm_q.weight") or k.endswith("norm_k.weight") or k.endswith("norm3.weight"):
-            sd[k] = torch.ones(v)
-    qa, mlp = synth.make_reward_state_dicts(cfg.dim, 1)
-    inp = synth.make_inputs(cfg, latent, 2, text_tokens=512)
+    cfg, inp = sample_inputs()
     times = []
     with torch.no_grad():
         for _ in range(repeats):
             t0 = time.perf_counter()
-            logit, _ = O.pavrm_reward(sd, cfg, qa, mlp, inp["x"], inp["t"], inp["context"], inp["seq_len"],
-                                      selected_layers=(blocks,), num_blocks=blocks)
+            logit, feats = O.pavrm_reward(sd, cfg, qa, mlp, inp["x"], inp["t"], inp["context"], inp["seq_len"],
+                                          selected_layers=(NUM_BLOCKS,), num_blocks=NUM_BLOCKS)
             times.append(time.perf_counter() - t0)
-    return inp["seq_len"], times, float(logit)
+    return inp["seq_len"], times, float(logit), feats
 
 
-def _shapes_14b(cfg):
+def synthetic_cpu_weights():
+    """14B-dims state dict for the TIMING-only reference arm: values do not matter, so tensors of one shape share
+    storage (reads still stream the full matrix per use) — building 2.8 G random fp32 parameters would take longer than
+    the measurement."""
     from oracle import synth
-    tiny = synth.WanConfig(**{**cfg.kwargs(), "num_layers": 1})
-    # shapes from a 1-layer dict, replicated per block, without materialising random weights twice
+    cfg = synth.cfg_14b("t2v", layers=NUM_BLOCKS)
+    g = torch.Generator().manual_seed(0)
     d, f = cfg.dim, cfg.ffn_dim
     shp = {"patch_embedding.weight": (d, cfg.in_dim, 1, 2, 2), "patch_embedding.bias": (d,),
            "text_embedding.0.weight": (d, cfg.text_dim), "text_embedding.0.bias": (d,), "text_embedding.2.weight": (d, d),
@@ -127,28 +166,79 @@ def _shapes_14b(cfg):
         shp[p + "ffn.0.weight"], shp[p + "ffn.0.bias"] = (f, d), (f,)
         shp[p + "ffn.2.weight"], shp[p + "ffn.2.bias"] = (d, f), (d,)
         shp[p + "modulation"] = (1, 6, d)
-    del tiny
-    return shp
+    sd, by_shape = {}, {}
+    for k, v in shp.items():
+        if len(v) > 1:
+            if v not in by_shape:
+                by_shape[v] = torch.empty(v).uniform_(-0.02, 0.02, generator=g)
+            sd[k] = by_shape[v]
+        else:
+            sd[k] = torch.zeros(v)
+        if k.endswith("norm_q.weight") or k.endswith("norm_k.weight") or k.endswith("norm3.weight"):
+            sd[k] = torch.ones(v)
+    qa, mlp = synth.make_reward_state_dicts(cfg.dim, 1)
+    return sd, qa, mlp
+
+
+SAMPLE_DESC = ("oracle port (torch CPU fp32) of the SAME workload architecture and depth — 14B dims, 8 blocks + reward head — "
+               "on a bounded sample: latent 16x3x32x52 -> 1248 tokens (attention cost grows with L^2: a short clip flatters the CPU)")
 
 
 def run_reference(args):
-    """`--impl reference`: the reference algorithm's CPU implementation (oracle port — the reference is
-    Python/PyTorch and is not present on the GPU box) with all host threads, bounded sample per step."""
+    """`--impl reference`: the reference algorithm's CPU implementation (oracle port — the reference is Python/PyTorch and
+    is not present on the GPU box) with all host threads; every step = one pass over the bounded sample."""
     rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
     if rank != 0:
         return
     cores = os.cpu_count() or 1
     threads = min(cores, 64)
-    L, _, _ = cpu_sample(threads, repeats=max(1, min(args.warmup, 1)))
-    L, times, _ = cpu_sample(threads, repeats=max(1, args.steps))
+    sd, qa, mlp = synthetic_cpu_weights()
+    cpu_oracle_pass(sd, qa, mlp, threads, repeats=max(1, min(args.warmup, 1)))
+    steps = max(1, min(args.steps, 10))                       # bounded: ~3-4 s per pass on 16 cores
+    L, times, _, _ = cpu_oracle_pass(sd, qa, mlp, threads, repeats=steps)
     ms = 1e3 * sum(times) / len(times)
     val = L / (ms / 1e3)
-    sample = f"14B arch, {NUM_BLOCKS} blocks + reward head, fp32, latent 16x3x30x52 -> {L} tokens (attention cost grows with L^2: a short clip flatters the CPU)"
     print(json.dumps({"impl": "reference", "metric": "dit_tokens_per_s", "value": val, "unit": "tokens/s", "n_gpus": args.gpus,
                       "steps": len(times), "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong",
-                      "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": {"workload": WORKLOAD, "sample": sample},
-                      "cpu_baseline": {"value": val, "unit": "tokens/s", "cores": threads, "kind": "port", "sample": sample},
+                      "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": bench_config(max(world, args.gpus)),
+                      "cpu_baseline": {"value": val, "unit": "tokens/s", "cores": threads, "kind": "port", "sample": SAMPLE_DESC},
                       "e2e": {"value": val, "unit": "tokens/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+
+
+# ---------------------------------------------------------------------------------------------------
+# GPU baseline: the oracle port on CUDA with eager PyTorch kernels (cuBLAS bf16 + flash-attn 2), BASELINE.md §2.2
+# ---------------------------------------------------------------------------------------------------
+def gpu_eager_baseline(sd_dev, qa_dev, mlp_dev, x_dev, t_dev, ctx_dev, L, ours_ms, steps=3):
+    from oracle import synth
+    from oracle import wan_oracle as O
+    try:
+        import flash_attn  # noqa: F401
+    except Exception as e:
+        return {"unavailable": f"flash_attn import failed: {type(e).__name__}: {e}"}
+    cfg = synth.cfg_14b("t2v", layers=NUM_BLOCKS)
+
+    def one():
+        with torch.no_grad():
+            logit, _ = O.pavrm_reward(sd_dev, cfg, qa_dev, mlp_dev, [x_dev], t_dev, [ctx_dev], L, selected_layers=(NUM_BLOCKS,),
+                                      num_blocks=NUM_BLOCKS, autocast_dtype=torch.bfloat16, native=True)
+        return logit
+    try:
+        logit = one()
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(steps):
+            one()
+        b.record()
+        torch.cuda.synchronize()
+        ms = a.elapsed_time(b) / steps
+    except Exception as e:
+        return {"unavailable": f"{type(e).__name__}: {str(e)[:200]}"}
+    return {"what": "oracle port on this GPU with eager PyTorch kernels: bf16 F.linear (cuBLAS, weights pre-cast once), "
+                    "flash_attn_func (FA2 2.8), ATen LayerNorm / RMSNorm, float64 RoPE as the reference does — same workload, same weights",
+            "ms_per_step": ms, "value": L / (ms * 1e-3), "unit": "tokens/s", "reward_logit": float(logit),
+            "speedup_ours_over_eager": ms / ours_ms}
 
 
 # ---------------------------------------------------------------------------------------------------
@@ -224,6 +314,16 @@ def run_ours(args):
             ms = float(tt)
         return ms, t0, t1
 
+    # ---- warm-up; at N > 1 the sequence-parallel parity checks run here (they exercise NCCL, the symmetric-memory exchange,
+    #      the training all-to-all path and the sharded optimizer on this very process group) -----------------------------
+    parity = {}
+    if world > 1 and not args.no_parity:
+        sys.path.insert(0, os.path.join(ROOT, "tests"))
+        try:
+            import sp_check
+            parity.update(sp_check.run_checks(world, rank, verbose=False))
+        except Exception as e:
+            parity["sp_checks_error"] = f"{type(e).__name__}: {str(e)[:300]}"
     for _ in range(max(args.warmup, 3)):
         step_resident()
     step_e2e()
@@ -235,6 +335,81 @@ def run_ours(args):
     clocks = sampler.stop(t0, t1) if sampler else None
     ms_e2e, _, _ = timed(step_e2e, args.steps)
     logit = float(logit_host)
+    per_step = ms / args.steps
+
+    # ---- same-weights parity on the bounded sample (and the CPU baseline it doubles as) ------------------------------
+    cpu_base = None
+    if not args.no_cpu and not args.no_parity:
+        try:
+            cfg_s, inp_s = sample_inputs()
+            xs = [u.to(dev) for u in inp_s["x"]]
+            cs = [c.to(dev) for c in inp_s["context"]]
+            ts = inp_s["t"].to(dev)
+            Ls = inp_s["seq_len"]
+            for _ in range(2):
+                lg, fg = scorer.score(xs, ts, cs, Ls, return_features=True)
+            ms_s, _, _ = timed(lambda: scorer.score(xs, ts, cs, Ls), 5)
+            fg_cpu = fg.float().cpu()
+            if rank == 0:
+                sd = {k: v.detach().float().cpu() for k, v in m.state_dict().items()}
+                qa_sd = {k: v.detach().float().cpu() for k, v in qa.state_dict().items()}
+                mlp_sd = {k: v.detach().float().cpu() for k, v in mlp.state_dict().items()}
+                cores = min(os.cpu_count() or 1, 64)
+                _, times, logit_o, feats_o = cpu_oracle_pass(sd, qa_sd, mlp_sd, cores)
+                del sd
+                a, b = fg_cpu.flatten().double(), feats_o.flatten().double()
+                cos = float(torch.dot(a, b) / (a.norm() * b.norm()))
+                rel = float((a - b).abs().max() / b.abs().max())
+                dl = abs(float(lg) - logit_o)
+                parity["same_weights_14b"] = {
+                    "what": f"same weights on both sides: oracle (CPU fp32) vs GPU, 14B dims, {NUM_BLOCKS} blocks + reward head, {Ls} tokens"
+                            + (f", GPU side Ulysses SP={world}" if world > 1 else ""),
+                    "features_cos": cos, "features_max_rel": rel, "logit_gpu": float(lg), "logit_oracle": logit_o, "dlogit": dl,
+                    "tolerance": {"cos_min": 0.999, "max_rel": 2e-2, "logit_abs": 1e-2},
+                    "ok": bool(cos >= 0.999 and rel <= 2e-2 and dl <= 1e-2)}
+                cpu_base = {"value": Ls / times[0], "unit": "tokens/s", "cores": cores, "kind": "port",
+                            "sample": SAMPLE_DESC + f"; 1 pass = {times[0]:.1f} s",
+                            "gpu_same_sample": {"value": Ls / (ms_s / 5 * 1e-3), "unit": "tokens/s", "ms_per_pass": ms_s / 5,
+                                                "note": "this arm on the CPU leg's exact sample and weights: the like-for-like ratio is gpu_same_sample / cpu_baseline"}}
+            del xs, cs, fg
+        except Exception as e:  # the GPU line must not be lost to a host-side problem
+            parity["same_weights_14b"] = {"ok": False, "error": f"{type(e).__name__}: {str(e)[:300]}"}
+    barrier()
+
+    # ---- eager-PyTorch GPU baseline (N = 1) ---------------------------------------------------------------------------------
+    gpu_base = None
+    if world == 1 and not args.no_gpu_baseline:
+        try:
+            keep32 = ("time_embedding", "time_projection", "norm", "modulation", "bias")
+            sd_dev = {k: (v.detach() if any(s in k for s in keep32) else v.detach().to(torch.bfloat16)) for k, v in m.state_dict().items()}
+            qa_dev = {k: v.detach() for k, v in qa.state_dict().items()}
+            mlp_dev = {k: v.detach() for k, v in mlp.state_dict().items()}
+            gpu_base = gpu_eager_baseline(sd_dev, qa_dev, mlp_dev, x_dev, t_dev, ctx_dev, L, per_step)
+            if "reward_logit" in gpu_base:
+                gpu_base["dlogit_vs_ours"] = abs(gpu_base["reward_logit"] - logit)
+            del sd_dev
+        except Exception as e:
+            gpu_base = {"unavailable": f"{type(e).__name__}: {str(e)[:200]}"}
+
+    # ---- free the scoring model, then the headline: PRFL 720P training step ---------------------------------------------------
+    del scorer, m, qa, mlp
+    import gc
+    gc.collect()
+    torch.cuda.empty_cache()
+    prfl = None
+    if not args.no_prfl:
+        sys.path.insert(0, os.path.join(ROOT, "tools"))
+        try:
+            import prfl_step
+            Lp = 21 * 45 * 80
+            blocks = args.prfl_blocks or prfl_step.fit_blocks(world, Lp)
+            prfl = prfl_step.measure(blocks, (0, 2), prfl_step.LATENT_720P, steps=args.prfl_steps, i2v=True, opt=True)
+            prfl["metric"] = "PRFL train s/step (BASELINE.json headline), I2V 720Px81f, 14B dims"
+            if blocks < 40:
+                prfl["note"] = (f"{blocks} of 40 VGM blocks: the largest depth whose bf16 weights + 1/{world} fp32 master/AdamW shards + "
+                                "checkpointed activations fit 180 GB at this N; per-block cost is depth-independent")
+        except Exception as e:
+            prfl = {"error": f"{type(e).__name__}: {str(e)[:400]}"}
 
     if rank == 0:
         pk = peaks()
@@ -243,35 +418,29 @@ def run_ours(args):
         heads_local = HEADS // world
         attn_flops = 4.0 * L * L * HD * heads_local                      # algorithmic, per launch
         achieved = attn_flops / (attn_avg * 1e-3) / 1e12 if attn_avg > 0 else 0.0
-        per_step = ms / args.steps
+        traffic, traffic_src = traffic_from_profiles() if world == 1 else (None, None)
+        parity["reward_logit_full_workload"] = logit
         line = {
             "metric": "dit_tokens_per_s", "value": L / (per_step * 1e-3), "unit": "tokens/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": per_step, "higher_is_better": True, "scaling": "strong",
-            "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "parallelism": f"ulysses_sp{world}", "weights": "random init",
-                       "l2": "per-step working set (5.6 GB bf16 weights + >2 GB activations) >> 126 MB L2; no explicit flush",
-                       "reward_logit": logit},
+            "vs_baseline": None, "dtype": "bf16", "data": "synthetic", "config": bench_config(world),
             "e2e": {"value": L / (ms_e2e / args.steps * 1e-3), "unit": "tokens/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4},
             "gpu_launches": int(launches),
             "clocks": clocks,
             "roofline": {"kernel": "attn_fwd_kernel (self-attention fwd, tcgen05)", "bound": "tensor", "achieved": achieved,
                          "peak": pk["tf_sust"], "unit": "TFLOP/s", "frac": achieved / pk["tf_sust"],
-                         # DRAM bytes per launch from the committed `ncu --set full` capture of this kernel at this shape
-                         # (profiles/r01_ncu_full_v2.csv: 1.049 GB read + 0.462 GB written; algorithmic Q,K,V,O = 1.342 GB;
-                         # the first capture of the round, r01_ncu_full_attn_gemm.csv, read 1.031 + 0.322 GB)
-                         "traffic": 1.511e9 if world == 1 else None,
+                         # DRAM bytes per launch of this kernel at this shape, read from the committed `ncu --set full` summary
+                         "traffic": traffic, "traffic_source": traffic_src, "algorithmic_bytes": 4.0 * L * HEADS * HD * 2,
                          "peak_source": pk["src"] + " sustained bf16", "launch_ms": attn_avg, "launches_timed": len(attn_ms),
                          "share_of_step": attn_avg * len(attn_ms) / max(ms, 1e-9)},
-            "step_tflops": (8 * 41.96e12 + 3.4e12 * 0) / world / (per_step * 1e-3) / 1e12,
+            "step_tflops": (8 * 41.96e12) / world / (per_step * 1e-3) / 1e12,
+            "parity": parity,
+            "prfl_step": prfl,
         }
-        if world == 1 and not args.no_cpu:
-            try:
-                cores = min(os.cpu_count() or 1, 64)
-                Ls, times, _ = cpu_sample(cores)
-                line["cpu_baseline"] = {"value": Ls / times[0], "unit": "tokens/s", "cores": cores, "kind": "port",
-                                        "sample": f"oracle (torch CPU fp32), 14B arch, {NUM_BLOCKS} blocks + reward head, latent 16x3x30x52 -> {Ls} tokens, 1 pass = {times[0]:.1f} s"}
-            except Exception as e:  # the GPU line must not be lost to a host-side problem
-                line["cpu_baseline"] = {"value": None, "unit": "tokens/s", "cores": 0, "kind": "port", "sample": f"failed: {e}"}
+        if cpu_base is not None:
+            line["cpu_baseline"] = cpu_base
+        if gpu_base is not None:
+            line["gpu_baseline"] = gpu_base
         print(json.dumps(line))
     if world > 1:
         dist.barrier()
@@ -284,7 +453,12 @@ if __name__ == "__main__":
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline / same-weights oracle leg")
+    ap.add_argument("--no-parity", action="store_true", help="skip the parity legs (profiling runs)")
+    ap.add_argument("--no-gpu-baseline", action="store_true", help="skip the eager-PyTorch (cuBLAS + flash-attn 2) leg")
+    ap.add_argument("--no-prfl", action="store_true", help="skip the PRFL 720P training-step leg")
+    ap.add_argument("--prfl-blocks", type=int, default=0, help="VGM depth of the training-step leg (0 = the largest that fits)")
+    ap.add_argument("--prfl-steps", type=int, default=2)
     a = ap.parse_args()
     if a.impl == "reference":
         run_reference(a)

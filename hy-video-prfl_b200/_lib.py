@@ -31,7 +31,7 @@ _SIGS = {
     "prfl_ln_mod_fwd": (C.c_int, [_p, _p, _p, _p, _p, _p, _p, _p, _i64, _i32, _f32, _i32, _p]),
     "prfl_ln_mod_split_fwd": (C.c_int, [_p, _p, _p, _p, _p, _i64, _i32, _f32, _p]),
     "prfl_rmsnorm_rope_fwd": (C.c_int, [_p, _i64, _p, _p, _p, _p, _i64, _p, _i64, _i32, _i64, _i64, _f32, _p]),
-    "prfl_gemm_bf16": (C.c_int, [_p, _i64, _i32, _p, _i64, _i32, _p, _i64, _p, _p, _p, _i64, _i32, _i32, _i32, _i32, _i32, _p]),
+    "prfl_gemm_bf16": (C.c_int, [_p, _i64, _i32, _p, _i64, _i32, _p, _i64, _p, _p, _p, _p, _i64, _i32, _i32, _i32, _i32, _i32, _p]),
     "prfl_attn_fwd_ws_bytes": (_i64, [_i32, _i32, _i32]),
     "prfl_attn_fwd_split_plan": (None, [_i32, _i32, _i32, _i32, _p]),
     "prfl_attn_fwd": (C.c_int, [_p, _i64, _i64, _p, _i64, _i64, _p, _i64, _i64, _p, _i64, _i64, _p, _i32, _i32, _i32, _f32, _p, _p]),
@@ -53,7 +53,7 @@ _SIGS = {
     "prfl_cast_f32_bf16": (C.c_int, [_p, _p, _i64, _p]),
     "prfl_unipc_step": (C.c_int, [_p, _p, _p, _f32, _p, _p, _p, _p, _f32, _p, _p, _p, _p, _p, _i64, _p]),
     "prfl_scale2_f32": (C.c_int, [_p, _f32, _p, _f32, _p, _i64, _p]),
-    "prfl_adamw_step": (C.c_int, [_p, _p, _p, _p, _p, _i64, _f32, _f32, _f32, _f32, _f32, _i32, _p]),
+    "prfl_adamw_step": (C.c_int, [_p, _p, _p, _p, _p, _p, _i64, _f32, _f32, _f32, _f32, _f32, _i32, _p]),
     "prfl_sumsq_f32": (C.c_int, [_p, _i64, _p, _p]),
     "prfl_a2a_pack": (C.c_int, [_p, _i64, _i64, _p, _i32, _i32, _i32, _i32, _p]),
 }

@@ -106,4 +106,4 @@ def load_optimizer(opt, model_dir: str) -> None:
         have = [n for n in os.listdir(model_dir) if n.startswith("optimizer-")]
         raise FileNotFoundError(f"{path} not found (checkpoint holds {have}); resharding optimizer state across a different "
                                 "world size is not supported")
-    opt.load_state_dict(load_file(path, device=str(opt.state[0]["master"].device)))
+    opt.load_state_dict(load_file(path, device=str(opt.units[0].master.device)))

@@ -437,13 +437,13 @@ extern "C" int prfl_attn_bwd(const void* q, int64_t q_ld_tok, int64_t q_ld_head,
   // to shrink its units to 32 queries to fit K, V in tensor memory next to two accumulators; that halves the latency
   // budget of the softmax-gradient stage (512 tensor cycles) and measures slower (33.5 ms): PRFL_ATTN_BWD_DKDV=ts for A/B.
   static const bool dkdv_ts = [] { const char* e = getenv("PRFL_ATTN_BWD_DKDV"); return e && e[0] == 't'; }();
-  static std::atomic<bool> attr_set{false};     // forward and autograd threads may race here: the call is idempotent
-  if (!attr_set.load(std::memory_order_acquire)) {
+  static unsigned long long attr_mask = 0;      // per-device bit mask; forward and autograd threads may race: the call is idempotent
+  if (device_needs_init(&attr_mask)) {
     cudaError_t e = cudaFuncSetAttribute(attn_bwd_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, BwdSmem<true>::BYTES);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(attn_bwd_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, BwdSmem<false>::BYTES);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(attn_bwd_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, BwdSmem<true>::BYTES);
     if (e != cudaSuccess) return cuda_fail(e, "attn_bwd: cudaFuncSetAttribute");
-    attr_set.store(true, std::memory_order_release);
+    device_mark_init(&attr_mask);
   }
   AttnBwdParams p;
   p.nlse2 = ws; p.ndelta = ws + (int64_t)H * Lp; p.Lq = Lq; p.Lk = Lk; p.Lp = Lp; p.scale = scale; p.scale_log2 = scale * 1.4426950408889634f;

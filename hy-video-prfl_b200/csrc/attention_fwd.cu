@@ -460,11 +460,11 @@ static int attn_fwd_launch(const void* q, int64_t q_ld_tok, int64_t q_ld_head, c
   if (rc != PRFL_OK) return rc;
   // measured at L = 32 760 x 40 heads: 0 % -> 20.98 ms, 25 % -> 18.34 ms, 37.5 % -> 19.40 ms, 50 % -> 19.96 ms
   auto kern = attn_fwd_kernel<0xAA>;
-  static std::atomic<bool> attr_set{false};     // forward and autograd threads may race here: the call is idempotent
-  if (!attr_set.load(std::memory_order_acquire)) {
+  static unsigned long long attr_mask = 0;      // per-device bit mask; forward and autograd threads may race: the call is idempotent
+  if (device_needs_init(&attr_mask)) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM);
     if (e != cudaSuccess) return cuda_fail(e, "attn_fwd: cudaFuncSetAttribute");
-    attr_set.store(true, std::memory_order_release);
+    device_mark_init(&attr_mask);
   }
   AttnFwdParams p;
   p.o = (__nv_bfloat16*)o; p.o_ld_tok = o_ld_tok; p.o_ld_head = o_ld_head; p.lse = lse; p.Lq = Lq; p.Lk = Lk;

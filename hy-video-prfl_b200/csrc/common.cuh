@@ -46,6 +46,11 @@ int make_tmap_3d(CUtensorMap* m, const void* base, uint64_t d0, uint64_t d1, uin
                  uint64_t stride2_bytes, uint32_t b0, uint32_t b1, uint32_t b2, int swizzle128, int elem_bytes = 2);
 int sm_count();
 void count_launch(int n = 1);   // feeds prfl_launch_count()
+// Per-DEVICE once-guard for cudaFuncSetAttribute(MaxDynamicSharedMemorySize): the attribute belongs to the device's
+// context, so a process that drives several GPUs must set it on each.  `mask` is a per-call-site atomic bit mask
+// (bit = device ordinal); returns true if this device still needs the call (idempotent if two threads race).
+bool device_needs_init(unsigned long long* mask_storage);
+void device_mark_init(unsigned long long* mask_storage);
 
 #ifdef __CUDACC__
 // ---------------------------------------------------------------------------------------------

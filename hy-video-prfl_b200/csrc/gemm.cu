@@ -33,6 +33,7 @@ struct GemmParams {
   int64_t ldc;
   const float* bias;
   const float* gate;
+  const float* resid;   // RESIDUAL: the stream that is read (out = resid + gate * bf16(acc + bias)); == out for the in-place form
   __nv_bfloat16* aux;   // DGELU: input (pre-activation); GELU / RESIDUAL: optional output bf16(acc + bias)
   int64_t ldaux;
   int M, N, K, epi, beta;
@@ -40,14 +41,29 @@ struct GemmParams {
   int group_m;   // raster: tiles are walked m-fastest inside groups of `group_m` row-tiles so a wave shares A and B panels in L2
 };
 
+// group_m > 0: groups of `group_m` row-tiles, all column tiles, walked m-fastest (the group's A panels stay in L2 while
+//              B streams once per group);
+// group_m < 0: the transpose — groups of `-group_m` column-tiles, all row tiles, walked n-fastest (the group's B panels
+//              stay in L2 while A streams once per group): fewer bytes when A (tokens) is the larger operand.
 __device__ __forceinline__ void tile_coords(int tile, int tiles_m, int tiles_n, int group_m, int& m_blk, int& n_blk) {
-  const int group = group_m * tiles_n;
-  const int g = tile / group;
-  const int first_m = g * group_m;
-  const int gm = min(tiles_m - first_m, group_m);
-  const int r = tile - g * group;
-  m_blk = first_m + r % gm;
-  n_blk = r / gm;
+  if (group_m > 0) {
+    const int group = group_m * tiles_n;
+    const int g = tile / group;
+    const int first_m = g * group_m;
+    const int gm = min(tiles_m - first_m, group_m);
+    const int r = tile - g * group;
+    m_blk = first_m + r % gm;
+    n_blk = r / gm;
+  } else {
+    const int group_n = -group_m;
+    const int group = group_n * tiles_m;
+    const int g = tile / group;
+    const int first_n = g * group_n;
+    const int gn = min(tiles_n - first_n, group_n);
+    const int r = tile - g * group;
+    n_blk = first_n + r % gn;
+    m_blk = r / gn;
+  }
 }
 
 template <bool A_T, bool B_T, int CG>
@@ -174,7 +190,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       if ((p.epi == PRFL_EPI_RESIDUAL || (p.epi == PRFL_EPI_F32 && p.beta)) && row_ok) {
         // the read-modify-write epilogue is latency-bound on the fp32 tile it updates: pull this thread's row segment
         // (1 KB = 8 lines) into L2 now, while the tile's main loop is still running
-        const float* o = reinterpret_cast<const float*>(p.out) + (int64_t)row * p.ldc + n_blk * BN;
+        const float* o = (p.epi == PRFL_EPI_RESIDUAL ? p.resid : reinterpret_cast<const float*>(p.out)) + (int64_t)row * p.ldc + n_blk * BN;
 #pragma unroll
         for (int j = 0; j < BN / 32; ++j)
           if (n_blk * BN + j * 32 < p.N) asm volatile("prefetch.global.L2 [%0];" ::"l"(o + j * 32));
@@ -247,6 +263,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         } else {
           float* o = reinterpret_cast<float*>(p.out) + (int64_t)row * p.ldc + col0;
           if (p.epi == PRFL_EPI_RESIDUAL) {
+            const float* rs = p.resid + (int64_t)row * p.ldc + col0;
             if (p.aux) {
               __nv_bfloat16* ax = p.aux + (int64_t)row * p.ldaux + col0;
 #pragma unroll
@@ -262,7 +279,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 #pragma unroll
             for (int j = 0; j < 32; j += 4) {
               if (col0 + j < p.N) {
-                float4 x4 = *reinterpret_cast<const float4*>(o + j);
+                float4 x4 = *reinterpret_cast<const float4*>(rs + j);
                 float4 g4 = p.gate ? __ldg(reinterpret_cast<const float4*>(p.gate + col0 + j)) : make_float4(1.f, 1.f, 1.f, 1.f);
                 x4.x += g4.x * bf16_round(v[j]); x4.y += g4.y * bf16_round(v[j + 1]);
                 x4.z += g4.z * bf16_round(v[j + 2]); x4.w += g4.w * bf16_round(v[j + 3]);
@@ -308,13 +325,13 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 
 template <bool A_T, bool B_T, int CG>
 static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, cudaStream_t st) {
-  static std::atomic<bool> attr_set{false};     // forward and autograd threads may race here: the call is idempotent
+  static unsigned long long attr_mask = 0;      // per-device bit mask; forward and autograd threads may race: the call is idempotent
   auto kern = gemm_bf16_kernel<A_T, B_T, CG>;
   constexpr int SMEM = GemmCfg<CG>::SMEM;
-  if (!attr_set.load(std::memory_order_acquire)) {
+  if (device_needs_init(&attr_mask)) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
     if (e != cudaSuccess) return cuda_fail(e, "gemm: cudaFuncSetAttribute");
-    attr_set.store(true, std::memory_order_release);
+    device_mark_init(&attr_mask);
   }
   const int total = p.tiles_m * p.tiles_n;          // tiles_m counts (128 * CG)-row tiles
   const int units = sm_count() / CG;
@@ -353,8 +370,8 @@ static int gemm_cta_group(int M) {
 using namespace prfl;
 
 extern "C" int prfl_gemm_bf16(const void* A, int64_t lda, int a_trans, const void* B, int64_t ldb, int b_trans, void* out,
-                              int64_t ldc, const float* bias, const float* gate, void* aux_bf16, int64_t ldaux, int M,
-                              int N, int K, int epi, int beta, prfl_stream_t stream) {
+                              int64_t ldc, const float* bias, const float* gate, const float* resid, void* aux_bf16,
+                              int64_t ldaux, int M, int N, int K, int epi, int beta, prfl_stream_t stream) {
   PRFL_CHECK_ARCH();
   PRFL_REQUIRE(M > 0 && N > 0 && K > 0 && N % 8 == 0, PRFL_E_SHAPE, "gemm: M=%d N=%d K=%d (need N%%8==0)", M, N, K);
   PRFL_REQUIRE(K % 8 == 0 || (a_trans && b_trans), PRFL_E_SHAPE, "gemm: K=%d must be a multiple of 8 unless both operands are transposed", K);
@@ -366,6 +383,7 @@ extern "C" int prfl_gemm_bf16(const void* A, int64_t lda, int a_trans, const voi
   PRFL_REQUIRE(!aux_bf16 || (ldaux >= N && ldaux % 8 == 0), PRFL_E_ALIGN, "gemm: ldaux=%lld", (long long)ldaux);
   PRFL_REQUIRE((reinterpret_cast<uintptr_t>(out) & 15) == 0 && (reinterpret_cast<uintptr_t>(bias) & 15) == 0 &&
                    (reinterpret_cast<uintptr_t>(gate) & 15) == 0 && (reinterpret_cast<uintptr_t>(aux_bf16) & 15) == 0 &&
+                   (reinterpret_cast<uintptr_t>(resid) & 15) == 0 &&
                    ((epi == PRFL_EPI_F32 || epi == PRFL_EPI_RESIDUAL) ? true : ldc % 8 == 0),
                PRFL_E_ALIGN, "gemm: out/bias/gate/aux must be 16-byte aligned");
   const int cg = gemm_cta_group(M);
@@ -378,6 +396,7 @@ extern "C" int prfl_gemm_bf16(const void* A, int64_t lda, int a_trans, const voi
   else rc = make_tmap_2d(&tmB, B, (uint64_t)N, (uint64_t)K, (uint64_t)ldb * 2, 64, 64, 1);
   if (rc != PRFL_OK) return rc;
   GemmParams p;
+  p.resid = (epi == PRFL_EPI_RESIDUAL && resid) ? resid : reinterpret_cast<const float*>(out);
   p.out = out; p.ldc = ldc; p.bias = bias; p.gate = gate; p.aux = (__nv_bfloat16*)aux_bf16; p.ldaux = ldaux;
   p.M = M; p.N = N; p.K = K; p.epi = epi; p.beta = beta;
   p.tiles_m = (M + BM * cg - 1) / (BM * cg); p.tiles_n = (N + BN - 1) / BN; p.num_kb = (K + BK - 1) / BK;
@@ -385,7 +404,7 @@ extern "C" int prfl_gemm_bf16(const void* A, int64_t lda, int a_trans, const voi
     const char* e = getenv("PRFL_GEMM_GROUP_M");
     return e ? atoi(e) : 0;
   }();
-  p.group_m = group_env > 0 ? group_env : 8;
+  p.group_m = group_env != 0 ? group_env : 8;
   cudaStream_t st = (cudaStream_t)stream;
   if (cg == 2) {
     if (!a_trans && !b_trans) return launch_gemm<false, false, 2>(tmA, tmB, p, st);

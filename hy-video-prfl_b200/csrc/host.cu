@@ -25,8 +25,22 @@ int cuda_fail(cudaError_t e, const char* what) {
   return PRFL_E_CUDA;
 }
 
-static int g_dev_state[64];  // 0 unknown, 1 ok, -1 wrong arch
-static int g_sm_count[64];
+static std::atomic<int> g_dev_state[64];  // 0 unknown, 1 ok, -1 wrong arch (written from the forward and the autograd threads)
+static std::atomic<int> g_sm_count[64];
+
+static int current_device_slot() {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) dev = 0;
+  return dev;
+}
+bool device_needs_init(unsigned long long* mask_storage) {
+  auto* m = reinterpret_cast<std::atomic<unsigned long long>*>(mask_storage);
+  return ((m->load(std::memory_order_acquire) >> current_device_slot()) & 1ull) == 0;
+}
+void device_mark_init(unsigned long long* mask_storage) {
+  auto* m = reinterpret_cast<std::atomic<unsigned long long>*>(mask_storage);
+  m->fetch_or(1ull << current_device_slot(), std::memory_order_release);
+}
 
 int check_device() {
   int dev = 0;
@@ -37,15 +51,15 @@ int check_device() {
     return PRFL_E_ARCH;
   }
   if (dev < 0 || dev >= 64) dev = 0;
-  if (g_dev_state[dev] == 0) {
+  if (g_dev_state[dev].load(std::memory_order_acquire) == 0) {
     cudaDeviceProp p;
     e = cudaGetDeviceProperties(&p, dev);
     if (e != cudaSuccess) return cuda_fail(e, "cudaGetDeviceProperties");
-    g_sm_count[dev] = p.multiProcessorCount;
-    g_dev_state[dev] = (p.major == 10) ? 1 : -1;
-    if (g_dev_state[dev] < 0) set_error("device %d is sm_%d%d; prfl_b200 is sm_100a only", dev, p.major, p.minor);
+    g_sm_count[dev].store(p.multiProcessorCount, std::memory_order_relaxed);
+    g_dev_state[dev].store((p.major == 10) ? 1 : -1, std::memory_order_release);
+    if (p.major != 10) set_error("device %d is sm_%d%d; prfl_b200 is sm_100a only", dev, p.major, p.minor);
   }
-  if (g_dev_state[dev] < 0) {
+  if (g_dev_state[dev].load(std::memory_order_acquire) < 0) {
     set_error("device %d is not sm_100; prfl_b200 is sm_100a only (no fallback)", dev);
     return PRFL_E_ARCH;
   }
@@ -56,7 +70,8 @@ int sm_count() {
   int dev = 0;
   cudaGetDevice(&dev);
   if (dev < 0 || dev >= 64) dev = 0;
-  return g_sm_count[dev] > 0 ? g_sm_count[dev] : 148;
+  const int n = g_sm_count[dev].load(std::memory_order_relaxed);
+  return n > 0 ? n : 148;
 }
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -129,7 +144,7 @@ int make_tmap_3d(CUtensorMap* m, const void* base, uint64_t d0, uint64_t d1, uin
 }  // namespace prfl
 
 extern "C" {
-int prfl_abi_version(void) { return 1; }
+int prfl_abi_version(void) { return 2; }
 const char* prfl_last_error_string(void) { return prfl::g_err; }
 int64_t prfl_launch_count(void) { return prfl::g_launches.load(); }
 void prfl_launch_count_reset(void) { prfl::g_launches.store(0); }

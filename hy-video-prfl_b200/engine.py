@@ -35,7 +35,8 @@ def _f(p):
 def block_forward(blk, x: torch.Tensor, em: torch.Tensor, ctx: torch.Tensor, seq_len_i: int, grid: Tuple[int, int, int],
                   first_block: bool, stash: Optional[Dict] = None, sample: int = 0) -> torch.Tensor:
     """One sample through one block.  x: [M, C] fp32 (updated in place), em: [6, C] fp32 (modulation + e),
-    ctx: [Lc, C] bf16.  With `stash` (a dict) every intermediate the backward needs is kept."""
+    ctx: [Lc, C] bf16.  With `stash` (a dict) every intermediate the backward needs is kept; x is then READ ONLY: the two
+    intermediate residual states are written to fresh buffers by the residual-epilogue GEMMs (`resid=`), no clones."""
     sa, ca = blk.self_attn, blk.cross_attn
     M, C = x.shape
     n, d = sa.num_heads, sa.head_dim
@@ -87,11 +88,15 @@ def block_forward(blk, x: torch.Tensor, em: torch.Tensor, ctx: torch.Tensor, seq
     a1 = a1.reshape(M, C)
     wo, bo = sa.o.operands()
     y1 = torch.empty(M, C, dtype=torch.bfloat16, device=x.device) if keep else None
-    x_in = x.clone() if keep else None
-    ops.gemm(a1, wo, bias=bo, epi=ops.EPI_RESIDUAL, out=x, gate=em[2], aux=y1)               # x += e2 * o(attn)
+    if keep:
+        x_in = x
+        x = ops.gemm(a1, wo, bias=bo, epi=ops.EPI_RESIDUAL, resid=x_in, gate=em[2], aux=y1)    # x1 = x_in + e2 * o(attn)
+    else:
+        x_in = None
+        ops.gemm(a1, wo, bias=bo, epi=ops.EPI_RESIDUAL, out=x, gate=em[2], aux=y1)           # x += e2 * o(attn)
 
     # ---- cross-attention ----
-    x1 = x.clone() if keep else None
+    x1 = x if keep else None
     if blk.cross_attn_norm:
         g3, b3 = _f(blk.norm3.weight), _f(blk.norm3.bias)
         if keep:
@@ -142,10 +147,13 @@ def block_forward(blk, x: torch.Tensor, em: torch.Tensor, ctx: torch.Tensor, seq
         a2 = o_g if a2 is None else a2 + o_g                                                 # model.py:269 (bf16 add)
     a2 = a2.reshape(M, C)
     wco, bco = ca.o.operands()
-    ops.gemm(a2, wco, bias=bco, epi=ops.EPI_RESIDUAL, out=x)                                 # x += o(cross)
+    if keep:
+        x = ops.gemm(a2, wco, bias=bco, epi=ops.EPI_RESIDUAL, resid=x1)                      # x2 = x1 + o(cross)
+    else:
+        ops.gemm(a2, wco, bias=bco, epi=ops.EPI_RESIDUAL, out=x)                             # x += o(cross)
 
     # ---- FFN ----
-    x2 = x.clone() if keep else None
+    x2 = x if keep else None
     if keep:
         h2, mean2, rstd2 = ops.ln_mod(x, em[3], em[4], None, None, blk.eps, save_stats=True)
     else:
@@ -173,17 +181,34 @@ def _wgrad(dy: torch.Tensor, x: torch.Tensor) -> torch.Tensor:
     return ops.gemm(dy, x, a_trans=True, b_trans=True, epi=ops.EPI_F32)
 
 
-def block_backward(blk, st: Dict, dx: torch.Tensor, need_ctx_grad: bool, need_w: bool = True, need_e: bool = True):
+def block_backward(blk, st: Dict, dx: torch.Tensor, need_ctx_grad: bool, need_w: bool = True, need_e: bool = True, sink=None):
     """dx: [M, C] fp32 gradient w.r.t. the block output; overwritten with the gradient w.r.t. the block input.
-    Returns (grads: name -> fp32 tensor, dem [6, C], dctx [Lc, C] fp32 or None)."""
+    Returns (grads: name -> fp32 tensor, dem [6, C], dctx [Lc, C] fp32 or None).  With a gradient `sink`
+    (sharding._BlockSink) the weight-gradient GEMMs write (or accumulate) straight into the sink's flat fp32 buffer —
+    fused operands (QKV, context K/V) as ONE [3C, C] / [2C, C] GEMM output — and only the small gradients are returned."""
     sa, ca = blk.self_attn, blk.cross_attn
     M, C = dx.shape
     n, d = sa.num_heads, sa.head_dim
     em = st["em"]
     g: Dict[str, torch.Tensor] = {}
     # frozen blocks (PRFL's reward model, Appendix B item 10): dgrad only, every weight-gradient kernel is skipped
-    wgrad = _wgrad if need_w else (lambda dy, x: None)
     colsum = ops.colsum if need_w else (lambda a: None)
+
+    def wgrad(names, dy, x):
+        """dW of the (fused) weight whose row blocks are `names`."""
+        if not need_w:
+            return
+        if sink is not None:
+            out, beta = sink.matrix_out(names)
+            ops.gemm(dy, x, a_trans=True, b_trans=True, epi=ops.EPI_F32, out=out, beta=beta)
+            return
+        dw = _wgrad(dy, x)
+        if len(names) == 1:
+            g[names[0]] = dw
+        else:
+            r = dw.shape[0] // len(names)
+            for j, nm in enumerate(names):
+                g[nm] = dw[j * r:(j + 1) * r]
 
     # ---- FFN ----
     w1, b1 = blk.ffn[0].operands()
@@ -195,11 +220,11 @@ def block_backward(blk, st: Dict, dx: torch.Tensor, need_ctx_grad: bool, need_w:
     dy2, de5 = ops.gate_bwd(dx, y2, em[5])
     del y2
     du = ops.gemm(dy2, w2, b_trans=True, epi=ops.EPI_BF16_DGELU, aux=st["u"])                # [M, ffn]
-    g["ffn.2.weight"] = wgrad(dy2, st["f"])
+    wgrad(("ffn.2.weight",), dy2, st["f"])
     g["ffn.2.bias"] = colsum(dy2)
     del dy2
     dh2 = ops.gemm(du, w1, b_trans=True, epi=ops.EPI_BF16)                                   # [M, C]
-    g["ffn.0.weight"] = wgrad(du, st["h2"])
+    wgrad(("ffn.0.weight",), du, st["h2"])
     g["ffn.0.bias"] = colsum(du)
     del du
     dsh2, dsc2 = ops.ln_mod_bwd(st["x2"], dh2, em[4], None, st["mean2"], st["rstd2"], dx, need_mod)
@@ -209,7 +234,7 @@ def block_backward(blk, st: Dict, dx: torch.Tensor, need_ctx_grad: bool, need_w:
     dyc, _ = ops.gate_bwd(dx, None, None)                                                     # bf16 cast of dx
     wco, _ = ca.o.operands()
     da2 = ops.gemm(dyc, wco, b_trans=True, epi=ops.EPI_BF16)
-    g["cross_attn.o.weight"] = wgrad(dyc, st["a2"])
+    wgrad(("cross_attn.o.weight",), dyc, st["a2"])
     g["cross_attn.o.bias"] = colsum(dyc)
     del dyc
     q2_3 = st["q2"].unflatten(1, (n, d))
@@ -229,8 +254,7 @@ def block_backward(blk, st: Dict, dx: torch.Tensor, need_ctx_grad: bool, need_w:
         g[nname] = ops.rmsnorm_rope_bwd_(cg["k_raw"], _f(cg["norm"].weight), None, None, dkv[:, :C], cg["rstd"], need_dw=need_w)
         wkv, _ = ca._kv_operands(cg["names"])
         if need_w:
-            dwkv = wgrad(dkv, cg["c_in"])                                                    # [2C, C]
-            g[f"cross_attn.{kn}.weight"], g[f"cross_attn.{vn}.weight"] = dwkv[:C], dwkv[C:]
+            wgrad((f"cross_attn.{kn}.weight", f"cross_attn.{vn}.weight"), dkv, cg["c_in"])   # [2C, C]
             dbkv = colsum(dkv)
             g[f"cross_attn.{kn}.bias"], g[f"cross_attn.{vn}.bias"] = dbkv[:C], dbkv[C:]
         if need_ctx_grad:
@@ -239,7 +263,7 @@ def block_backward(blk, st: Dict, dx: torch.Tensor, need_ctx_grad: bool, need_w:
     g["cross_attn.norm_q.weight"] = ops.rmsnorm_rope_bwd_(st["q2_raw"], _f(ca.norm_q.weight), None, None, dq2, st["rstd_q2"], need_dw=need_w)
     wcq, _ = ca.q.operands()
     dh3 = ops.gemm(dq2, wcq, b_trans=True, epi=ops.EPI_BF16)
-    g["cross_attn.q.weight"] = wgrad(dq2, st["h3"])
+    wgrad(("cross_attn.q.weight",), dq2, st["h3"])
     g["cross_attn.q.bias"] = colsum(dq2)
     del dq2, da2
     if blk.cross_attn_norm:
@@ -253,7 +277,7 @@ def block_backward(blk, st: Dict, dx: torch.Tensor, need_ctx_grad: bool, need_w:
     dy1, de2 = ops.gate_bwd(dx, st["y1"] if need_mod else None, em[2])
     wo, _ = sa.o.operands()
     da1 = ops.gemm(dy1, wo, b_trans=True, epi=ops.EPI_BF16)
-    g["self_attn.o.weight"] = wgrad(dy1, st["a1"])
+    wgrad(("self_attn.o.weight",), dy1, st["a1"])
     g["self_attn.o.bias"] = colsum(dy1)
     del dy1
     qkv = st["qkv"]
@@ -271,8 +295,8 @@ def block_backward(blk, st: Dict, dx: torch.Tensor, need_ctx_grad: bool, need_w:
         dvg = torch.zeros_like(dkg) if klen < L else torch.empty_like(dkg)
         dqg, _, _ = ops.attn_bwd(st["qg"], st["kg"][:klen], st["vg"][:klen], st["og"], dog, st["lse1"], dk=dkg[:klen], dv=dvg[:klen])
         dqkv = torch.empty(M, 3 * C, dtype=torch.bfloat16, device=dx.device)
-        for j, t in enumerate((dqg, dkg, dvg)):
-            dqkv[:, j * C:(j + 1) * C] = ulysses_gather_tokens(t, P).reshape(M, C)
+        for j, t in enumerate((dqg, dkg, dvg)):                                               # unpacked straight into the fused buffer
+            ulysses_gather_tokens(t, P, out=dqkv[:, j * C:(j + 1) * C].unflatten(1, (n, d)))
     del da1
     qk_raw = st["qk_raw"]
     g["self_attn.norm_q.weight"] = ops.rmsnorm_rope_bwd_(qk_raw[:, :C], _f(sa.norm_q.weight), st["cos"], st["sin"], dqkv[:, :C],
@@ -282,10 +306,9 @@ def block_backward(blk, st: Dict, dx: torch.Tensor, need_ctx_grad: bool, need_w:
     wqkv, _ = sa._qkv_operands()
     dh1 = ops.gemm(dqkv, wqkv, b_trans=True, epi=ops.EPI_BF16)                               # [M, C]
     if need_w:
-        dwqkv = wgrad(dqkv, st["h1"])                                                        # [3C, C]
+        wgrad(("self_attn.q.weight", "self_attn.k.weight", "self_attn.v.weight"), dqkv, st["h1"])   # [3C, C]
         dbqkv = colsum(dqkv)
         for j, nm in enumerate(("q", "k", "v")):
-            g[f"self_attn.{nm}.weight"] = dwqkv[j * C:(j + 1) * C]
             g[f"self_attn.{nm}.bias"] = dbqkv[j * C:(j + 1) * C]
     del dqkv
     dsh1, dsc1 = ops.ln_mod_bwd(st["x_in"], dh1, em[1], None, st["mean1"], st["rstd1"], dx, need_mod)
@@ -330,12 +353,19 @@ class BlockFn(torch.autograd.Function):
         need_ctx = ctx.needs_input_grad[2]
         need_w = any(ctx.needs_input_grad[8:])
         need_e = ctx.needs_input_grad[1]
+        unit = blk.__dict__.get("_prfl_unit")
+        sink = unit.sink if (unit is not None and need_w) else None     # resident bf16 block owned by a ShardedAdamW
+        if need_w and unit is not None and sink is None:
+            raise RuntimeError("a resident bf16 block has no fp32 gradient path through autograd: attach a sharding.ShardedAdamW "
+                               "(its gradient sink receives the weight gradients) or freeze the block")
+        if sink is not None:
+            sink.begin()
         tot: Dict[str, torch.Tensor] = {}
         dems, dctxs = [], []
         for i in range(B):
             st: Dict = {}
-            block_forward(blk, x[i].detach().clone(), em[i], cb[i].contiguous(), int(ctx.seq_lens[i]), ctx.grids[i], ctx.first, st)
-            gi, dem, dctx = block_backward(blk, st, dx[i], need_ctx, need_w, need_e)
+            block_forward(blk, x[i].detach(), em[i], cb[i].contiguous(), int(ctx.seq_lens[i]), ctx.grids[i], ctx.first, st)
+            gi, dem, dctx = block_backward(blk, st, dx[i], need_ctx, need_w, need_e, sink)
             del st
             for k, v in gi.items():
                 if v is not None:
@@ -349,9 +379,16 @@ class BlockFn(torch.autograd.Function):
             de = None
         dctx = torch.stack(dctxs).to(context.dtype) if need_ctx else None
         pg = []
-        for nm, p in zip(ctx.names, ctx.blk.parameters()):
-            gr = tot.get(nm)
-            pg.append(None if gr is None else gr.reshape(p.shape).to(p.dtype))
+        if sink is not None:
+            for nm, gr in tot.items():                                                        # biases, norm weights, modulation -> root unit
+                if gr is not None:
+                    sink.small(nm, gr)
+            sink.end()                                                                        # reduce-scatter on the side stream
+            pg = [None] * len(ctx.names)
+        else:
+            for nm, p in zip(ctx.names, ctx.blk.parameters()):
+                gr = tot.get(nm)
+                pg.append(None if gr is None else gr.reshape(p.shape).to(p.dtype))
         return (dx, de, dctx, None, None, None, None, None, *pg)
 
 

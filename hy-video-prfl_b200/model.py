@@ -40,12 +40,22 @@ T5_CONTEXT_TOKEN_NUMBER = 512
 # bf16 operand cache: fp32 master parameters -> bf16 copies, refreshed when the parameter changes
 # (what torch.autocast re-does on every Linear call in the reference).
 # ------------------------------------------------------------------------------------------------
+_WEIGHT_EPOCH = [0]
+
+
+def bump_weight_epoch():
+    """Invalidate every derived operand (concatenated / split / fp32-bias copies, PreparedContext K/V are the caller's):
+    called by `sharding.ShardedAdamW.step()`, whose updates land in the flat buffers the parameters are views of and
+    therefore do not bump the parameters' own version counters."""
+    _WEIGHT_EPOCH[0] += 1
+
+
 class _OperandCache:
     def __init__(self):
         self._store = {}
 
     def get(self, key, params: Sequence[torch.Tensor], build):
-        ver = tuple((p.data_ptr(), p._version) for p in params)
+        ver = (_WEIGHT_EPOCH[0],) + tuple((p.data_ptr(), p._version) for p in params)
         hit = self._store.get(key)
         if hit is not None and hit[0] == ver:
             return hit[1]
@@ -58,6 +68,18 @@ class _OperandCache:
 
 
 def _cat_bf16(ws: Sequence[torch.Tensor]) -> torch.Tensor:
+    """The [sum rows, K] bf16 operand of one or several weights.  Resident bf16 parameters (sharding.ResidentUnit) that are
+    adjacent in their flat buffer ARE the operand: a view, no copy."""
+    if all(p.dtype == torch.bfloat16 and p.is_contiguous() for p in ws):
+        if len(ws) == 1:
+            return ws[0].detach().reshape(ws[0].shape[0], -1)
+        k = ws[0][0].numel()
+        adjacent = all(a.data_ptr() + a.numel() * 2 == b.data_ptr() and b[0].numel() == k and
+                       a.untyped_storage().data_ptr() == b.untyped_storage().data_ptr() for a, b in zip(ws, ws[1:]))
+        if adjacent:
+            rows = sum(p.shape[0] for p in ws)
+            return torch.as_strided(ws[0].detach(), (rows, k), (k, 1))
+        return torch.cat([p.detach().reshape(p.shape[0], -1) for p in ws], dim=0)
     w = torch.cat([p.detach().reshape(p.shape[0], -1) for p in ws], dim=0).float().contiguous()
     return ops.cast_bf16(w)
 

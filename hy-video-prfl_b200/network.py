@@ -116,7 +116,7 @@ class QueryAttention(nn.Module):
         if len(shape) == 4:
             out = out.view(shape[0], bsz // shape[0], -1).mean(dim=0)
         if self.return_type == "query":
-            out = out + self.queries.float().unsqueeze(0).expand(bsz, -1, -1)              # [B, 1, C] (network.py:103-104)
+            out = out + queries.unsqueeze(0).expand(bsz, -1, -1)                           # [B, 1, C] (network.py:73-75,103-104: incl. + e)
         return out
 
 

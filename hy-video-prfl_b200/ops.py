@@ -116,9 +116,11 @@ def rmsnorm_rope_(x: torch.Tensor, w: torch.Tensor, cos: Optional[torch.Tensor],
 
 def gemm(a: torch.Tensor, b: torch.Tensor, *, a_trans: bool = False, b_trans: bool = False,
          bias: Optional[torch.Tensor] = None, epi: int = EPI_BF16, out: Optional[torch.Tensor] = None,
-         gate: Optional[torch.Tensor] = None, aux: Optional[torch.Tensor] = None, beta: bool = False) -> torch.Tensor:
+         gate: Optional[torch.Tensor] = None, aux: Optional[torch.Tensor] = None, beta: bool = False,
+         resid: Optional[torch.Tensor] = None) -> torch.Tensor:
     """acc[m, n] = sum_k A(m, k) B(n, k) on tcgen05 with a fused epilogue.
-    a: [M, K] (or [K, M] if a_trans), b: [N, K] (or [K, N] if b_trans); inner stride 1, row stride free."""
+    a: [M, K] (or [K, M] if a_trans), b: [N, K] (or [K, N] if b_trans); inner stride 1, row stride free.
+    EPI_RESIDUAL: out = resid + gate * bf16(acc + bias); resid defaults to out (in place)."""
     _req(a, bf16, "gemm.a")
     _req(b, bf16, "gemm.b")
     assert a.dim() == 2 and b.dim() == 2 and a.stride(1) == 1 and b.stride(1) == 1
@@ -127,8 +129,11 @@ def gemm(a: torch.Tensor, b: torch.Tensor, *, a_trans: bool = False, b_trans: bo
     assert K == Kb, (a.shape, b.shape, a_trans, b_trans)
     f32_out = epi in (EPI_F32, EPI_RESIDUAL)
     if out is None:
-        assert epi != EPI_RESIDUAL and not beta
+        assert (epi != EPI_RESIDUAL or resid is not None) and not beta
         out = torch.empty(M, N, dtype=f32 if f32_out else bf16, device=a.device)
+    if resid is not None:
+        _req(resid, f32, "gemm.resid")
+        assert epi == EPI_RESIDUAL and resid.shape == (M, N) and resid.stride(1) == 1 and resid.stride(0) == out.stride(0)
     _req(out, f32 if f32_out else bf16, "gemm.out")
     assert out.shape == (M, N) and out.stride(1) == 1
     if bias is not None:
@@ -144,7 +149,7 @@ def gemm(a: torch.Tensor, b: torch.Tensor, *, a_trans: bool = False, b_trans: bo
         ldaux = aux.stride(0)
     with _timed("gemm"):
         check(lib().prfl_gemm_bf16(_p(a), a.stride(0), int(a_trans), _p(b), b.stride(0), int(b_trans), _p(out), out.stride(0),
-                                   _p(bias), _p(gate), _p(aux), ldaux, M, N, K, epi, int(beta), _stream()), "prfl_gemm_bf16")
+                                   _p(bias), _p(gate), _p(resid), _p(aux), ldaux, M, N, K, epi, int(beta), _stream()), "prfl_gemm_bf16")
     return out
 
 
@@ -432,14 +437,19 @@ def scale2(g, a: float, b: Optional[float] = None):
 # ------------------------------------------------------------------------------------------------
 # sharded optimizer
 # ------------------------------------------------------------------------------------------------
-def adamw_step_(grad, master, exp_avg, exp_avg_sq, step: int, lr: float, betas, eps: float, weight_decay: float, clip_coef=None):
-    """In-place AdamW on one fp32 shard (all four tensors flat, same length).  clip_coef: 0-dim CUDA fp32 tensor or None."""
+def adamw_step_(grad, master, exp_avg, exp_avg_sq, step: int, lr: float, betas, eps: float, weight_decay: float, clip_coef=None,
+                bf16_out: Optional[torch.Tensor] = None):
+    """In-place AdamW on one fp32 shard (all four tensors flat, same length).  clip_coef: 0-dim CUDA fp32 tensor or None.
+    bf16_out: flat bf16 tensor of the same length receiving bf16(master) in the same pass (the resident compute copy)."""
     for t, n in ((grad, "grad"), (master, "master"), (exp_avg, "exp_avg"), (exp_avg_sq, "exp_avg_sq")):
         _req(t, f32, "adamw_step." + n)
         assert t.is_contiguous() and t.numel() == master.numel()
     if clip_coef is not None:
         _req(clip_coef, f32, "adamw_step.clip_coef")
-    check(lib().prfl_adamw_step(_p(grad), _p(master), _p(exp_avg), _p(exp_avg_sq), _p(clip_coef), master.numel(), float(lr),
+    if bf16_out is not None:
+        _req(bf16_out, bf16, "adamw_step.bf16_out")
+        assert bf16_out.is_contiguous() and bf16_out.numel() == master.numel()
+    check(lib().prfl_adamw_step(_p(grad), _p(master), _p(exp_avg), _p(exp_avg_sq), _p(clip_coef), _p(bf16_out), master.numel(), float(lr),
                                 float(betas[0]), float(betas[1]), float(eps), float(weight_decay), int(step), _stream()), "prfl_adamw_step")
 
 
@@ -449,3 +459,49 @@ def sumsq_(x, acc):
     _req(acc, torch.float64, "sumsq.acc")
     check(lib().prfl_sumsq_f32(_p(x.contiguous()), x.numel(), _p(acc), _stream()), "prfl_sumsq_f32")
     return acc
+
+
+# ------------------------------------------------------------------------------------------------
+# NVTX ranges per kernel family: PRFL_NVTX=1 wraps every op of this module in a range named
+# "prfl/<family>/<op>" so that nsys / ncu --nvtx timelines group launches by family; off by default (two extra
+# host calls per launch).
+# ------------------------------------------------------------------------------------------------
+NVTX_FAMILIES = {
+    "norm": ("ln_mod", "ln_mod_split", "rmsnorm_rope_", "ln_mod_bwd", "rmsnorm_rope_bwd_", "colsum", "gate_bwd", "cast_bf16"),
+    "gemm": ("gemm",),
+    "attention": ("attn_fwd", "attn_bwd", "attn_fwd_p2p"),
+    "exchange": ("a2a_pack", "a2a_scatter_p2p"),
+    "patch": ("patchify", "patchify_bwd", "unpatchify", "unpatchify_bwd"),
+    "reward": ("sq_pool", "sq_pool_bwd"),
+    "scheduler": ("unipc_step", "scale2"),
+    "optimizer": ("adamw_step_", "sumsq_"),
+}
+
+
+def install_nvtx(enable: Optional[bool] = None) -> bool:
+    import functools
+    import os
+    if enable is None:
+        enable = os.environ.get("PRFL_NVTX", "0") == "1"
+    if not enable or globals().get("_NVTX_ON"):
+        return bool(globals().get("_NVTX_ON"))
+    g = globals()
+    for fam, names in NVTX_FAMILIES.items():
+        for n in names:
+            fn = g[n]
+
+            def wrap(fn=fn, label=f"prfl/{fam}/{n.rstrip('_')}"):
+                @functools.wraps(fn)
+                def inner(*a, **k):
+                    torch.cuda.nvtx.range_push(label)
+                    try:
+                        return fn(*a, **k)
+                    finally:
+                        torch.cuda.nvtx.range_pop()
+                return inner
+            g[n] = wrap()
+    g["_NVTX_ON"] = True
+    return True
+
+
+install_nvtx()

@@ -92,14 +92,19 @@ def _pack_heads(x: torch.Tensor, P: int) -> torch.Tensor:
     return x.reshape(L, P, H // P, d).permute(1, 0, 2, 3).contiguous()
 
 
-def _unpack_heads(packed: torch.Tensor, P: int) -> torch.Tensor:
-    """wire layout [P, L_loc, H/P, d] (source rank major) -> [L_loc, H, d]."""
+def _unpack_heads(packed: torch.Tensor, P: int, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """wire layout [P, L_loc, H/P, d] (source rank major) -> [L_loc, H, d] (`out`: a strided [L_loc, H, d] destination)."""
     _, L, Hl, d = packed.shape
     if packed.is_cuda:
         from . import ops
-        out = torch.empty(L, P * Hl, d, dtype=packed.dtype, device=packed.device)
+        if out is None:
+            out = torch.empty(L, P * Hl, d, dtype=packed.dtype, device=packed.device)
         return ops.a2a_pack(out, packed, P, unpack=True)
-    return packed.permute(1, 0, 2, 3).reshape(L, P * Hl, d).contiguous()
+    res = packed.permute(1, 0, 2, 3).reshape(L, P * Hl, d).contiguous()
+    if out is not None:
+        out.copy_(res)
+        return out
+    return res
 
 
 def _a2a(buf: torch.Tensor) -> torch.Tensor:
@@ -115,12 +120,12 @@ def ulysses_scatter_tokens(x: torch.Tensor, P: int) -> torch.Tensor:
     return _a2a(_pack_heads(x, P)).view(P * L, H // P, d)
 
 
-def ulysses_gather_tokens(x: torch.Tensor, P: int) -> torch.Tensor:
+def ulysses_gather_tokens(x: torch.Tensor, P: int, out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """scatter tokens / gather heads: [L, H/P, d] -> local [L/P, H, d] (communication.py:91-123).
-    The send buffer is x itself ([P, L/P, H/P, d] by token chunk)."""
+    The send buffer is x itself ([P, L/P, H/P, d] by token chunk).  `out`: optional strided destination view."""
     L, Hl, d = x.shape
     recv = _a2a(x.contiguous().view(P, L // P, Hl, d))
-    return _unpack_heads(recv, P)
+    return _unpack_heads(recv, P, out)
 
 
 class SeqAllToAll4D(torch.autograd.Function):
@@ -227,11 +232,21 @@ def get_p2p_ulysses(L: int, H: int, device) -> Optional[P2PUlysses]:
         return None
     key = (L, H, str(device))
     if key not in _p2p_cache:
+        obj, err = None, None
         try:
-            _p2p_cache[key] = P2PUlysses(L, H, device)
-        except Exception as e:  # no fabric / no peer access: keep NCCL
+            obj = P2PUlysses(L, H, device)
+        except Exception as e:  # no fabric / no peer access / out of memory on THIS rank
+            err = e
+        # the choice must be unanimous: a rank that fell back to NCCL while its peers wait in a symmetric-memory barrier
+        # would deadlock the group, so agree on the outcome (MIN over the SP group) before committing to either path
+        ok = torch.tensor([0 if obj is None else 1], dtype=torch.int32, device=device)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=nccl_info.group)
+        if int(ok) == 0:
             import warnings
-            warnings.warn(f"prfl_b200: symmetric-memory Ulysses unavailable ({type(e).__name__}: {e}); using NCCL all-to-all")
+            why = f"{type(err).__name__}: {err}" if err is not None else "a peer rank could not set it up"
+            warnings.warn(f"prfl_b200: symmetric-memory Ulysses unavailable ({why}); using NCCL all-to-all on every rank")
+            del obj                                   # frees this rank's partially / fully created symmetric buffers
             _p2p_disabled = True
             return None
+        _p2p_cache[key] = obj
     return _p2p_cache[key]

@@ -94,6 +94,7 @@ class FlowUniPCMultistepScheduler:
             sigmas = shift * sigmas / (1 + (shift - 1) * sigmas)
         self.sigmas = sigmas.to("cpu")
         self.timesteps = sigmas * num_train_timesteps
+        self._timesteps_host = self.timesteps.tolist()          # float schedule until set_timesteps() (fm_solvers_unipc.py:103)
         self.model_outputs = [None] * solver_order
         self.timestep_list = [None] * solver_order
         self.lower_order_nums = 0
@@ -139,21 +140,26 @@ class FlowUniPCMultistepScheduler:
         timesteps = sigmas * self.config.num_train_timesteps
         sigmas = np.concatenate([sigmas, [0]]).astype(np.float32)
         self.sigmas = torch.from_numpy(sigmas).to("cpu")
-        self.timesteps = torch.from_numpy(timesteps).to(device=device, dtype=torch.int64)
+        ts_host = torch.from_numpy(timesteps).to(dtype=torch.int64)
+        self.timesteps = ts_host.to(device=device)
         self.num_inference_steps = len(timesteps)
         self.model_outputs = [None] * self.config.solver_order
         self.lower_order_nums = 0
         self.last_sample = None
         self._step_index = None
         self._begin_index = None
-        self._timesteps_host = [int(t) for t in timesteps.astype(np.int64)] if isinstance(timesteps, np.ndarray) else \
-            [int(t) for t in self.timesteps.tolist()]
+        self._timesteps_host = ts_host.tolist()                 # exact values of the schedule's own dtype (int64 here), no device sync
 
     def index_for_timestep(self, timestep, schedule_timesteps=None):
-        # fm_solvers_unipc.py:628-641, on the host copy of the schedule (no device sync per step)
-        ts = self._timesteps_host if schedule_timesteps is None else [int(t) for t in schedule_timesteps.tolist()]
-        t = int(timestep)
-        hits = [i for i, u in enumerate(ts) if u == t]
+        # fm_solvers_unipc.py:628-641 (exact `==` on the schedule's values, second hit if the value repeats), on the host
+        # copy of the schedule (no device sync per step).  No truncation: a float schedule (the constructor's
+        # `sigmas * num_train_timesteps`, dynamic shifting) has entries that share an integer part.
+        ts = self._timesteps_host if schedule_timesteps is None else schedule_timesteps.tolist()
+        if torch.is_tensor(timestep):
+            timestep = timestep.item()
+        if schedule_timesteps is not None and torch.is_tensor(schedule_timesteps) and schedule_timesteps.dtype.is_floating_point:
+            timestep = torch.tensor(timestep, dtype=schedule_timesteps.dtype).item()       # compare in the schedule's dtype, as torch's == does
+        hits = [i for i, u in enumerate(ts) if u == timestep]
         return hits[1 if len(hits) > 1 else 0]
 
     def _init_step_index(self, timestep):

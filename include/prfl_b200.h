@@ -105,8 +105,10 @@ int prfl_gate_bwd(const float* dx, const void* y_bf16, const float* gate, void* 
  *   PRFL_EPI_BF16       out_bf16[m,n]  = bf16(acc + bias[n])
  *   PRFL_EPI_BF16_GELU  out_bf16[m,n]  = bf16(gelu_tanh(bf16(acc + bias[n])))        (model.py:314)
  *   PRFL_EPI_F32        out_f32[m,n]   = acc + bias[n]        (beta=1: out_f32 += ...; wgrad accumulation)
- *   PRFL_EPI_RESIDUAL   out_f32[m,n]  += gate[n] * bf16(acc + bias[n])   gate NULL => 1
- *                       (fuses the gated residual adds model.py:348,352,355 into o / ffn.2)
+ *   PRFL_EPI_RESIDUAL   out_f32[m,n]   = resid[m,n] + gate[n] * bf16(acc + bias[n])   gate NULL => 1; resid NULL => out
+ *                       (fuses the gated residual adds model.py:348,352,355 into o / ffn.2; resid [M, N] f32 with the
+ *                       leading dimension of out: a separate input stream lets the checkpointed backward keep the
+ *                       block's intermediate residual states without cloning them first)
  *   PRFL_EPI_BF16_DGELU out_bf16[m,n]  = bf16(acc * gelu_tanh'(aux_bf16[m,n]))   (FFN backward; aux is an INPUT)
  * With PRFL_EPI_BF16_GELU or PRFL_EPI_RESIDUAL a non-NULL aux_bf16 [M, N] (ldaux) is an extra OUTPUT that receives
  * bf16(acc + bias[n]) — the pre-activation / the un-gated branch output the backward needs.
@@ -118,8 +120,8 @@ int prfl_gate_bwd(const float* dx, const void* y_bf16, const float* gate, void* 
 #define PRFL_EPI_RESIDUAL 3
 #define PRFL_EPI_BF16_DGELU 4
 int prfl_gemm_bf16(const void* A, int64_t lda, int a_trans, const void* B, int64_t ldb, int b_trans, void* out,
-                   int64_t ldc, const float* bias, const float* gate, void* aux_bf16, int64_t ldaux, int M, int N,
-                   int K, int epi, int beta, prfl_stream_t stream);
+                   int64_t ldc, const float* bias, const float* gate, const float* resid, void* aux_bf16, int64_t ldaux,
+                   int M, int N, int K, int epi, int beta, prfl_stream_t stream);
 
 /* ---- flash attention, bf16, head_dim 128, non-causal ------------------------------------------
  * Replaces flash_attn_varlen_func behind flash_attention() (attention.py:24-130) as called from
@@ -230,9 +232,13 @@ int prfl_scale2_f32(const float* g, float a, float* ya, float b, float* yb, int6
 /* ---- sharded optimizer ---------------------------------------------------------------------------
  * AdamW (decoupled weight decay, torch.optim.AdamW semantics; train_prfl.py:482-491, 825-830) on one rank's fp32 shard of
  * an FSDP unit: grad (already reduce-scattered), master weights and both moments, n elements each, updated in place by
- * one kernel.  clip_coef_dev: DEVICE pointer to the clip_grad_norm_ coefficient (NULL = 1); step = 1-based update count. */
-int prfl_adamw_step(const float* grad, float* master, float* exp_avg, float* exp_avg_sq, const float* clip_coef_dev, int64_t n,
-                    float lr, float beta1, float beta2, float eps, float weight_decay, int step, prfl_stream_t stream);
+ * one kernel.  clip_coef_dev: DEVICE pointer to the clip_grad_norm_ coefficient (NULL = 1); step = 1-based update count.
+ * master_bf16_out (may be NULL): n bf16 elements receiving bf16(master) in the same pass — this rank's slice of the resident
+ * bf16 operand buffer, all-gathered in bf16 afterwards (what torch.autocast re-derives from FSDP's fp32 all-gather,
+ * fsdp_utils.py:86-109, on every use). */
+int prfl_adamw_step(const float* grad, float* master, float* exp_avg, float* exp_avg_sq, const float* clip_coef_dev,
+                    void* master_bf16_out, int64_t n, float lr, float beta1, float beta2, float eps, float weight_decay, int step,
+                    prfl_stream_t stream);
 /* acc[0] (DEVICE double) += sum_i x[i]^2 — the local part of FSDP.clip_grad_norm_ (train_prfl.py:825). */
 int prfl_sumsq_f32(const float* x, int64_t n, double* acc, prfl_stream_t stream);
 

@@ -64,10 +64,16 @@ class WanConfig:
 class _Prec:
     """Emulates what `torch.autocast(dtype)` does to F.linear on the reference path."""
 
-    def __init__(self, autocast_dtype: Optional[torch.dtype]):
+    def __init__(self, autocast_dtype: Optional[torch.dtype], native: bool = False):
         self.dt = autocast_dtype
+        # native=True (bench.py's gpu_baseline leg only): run the low-precision ops for real on the tensors' device —
+        # F.linear in `dt` (cuBLAS on CUDA) and flash-attn 2 — instead of emulating their rounding in fp32.  This is
+        # the reference's own kernel stack (attention.py:113-127, nn.Linear under autocast) driven by this restatement.
+        self.native = native and autocast_dtype is not None
 
     def linear(self, x, w, b=None):
+        if self.native:
+            return F.linear(x.to(self.dt), w.to(self.dt), None if b is None else b.to(self.dt))
         if self.dt is None:
             return F.linear(x.to(w.dtype) if x.dtype != w.dtype else x, w, b)
         # autocast: inputs and params cast to the low dtype, fp32 accumulate, low-dtype output
@@ -95,7 +101,7 @@ def sinusoidal_embedding_1d(dim: int, position: torch.Tensor) -> torch.Tensor:
     half = dim // 2
     pos = position.to(torch.float64)
     inv = torch.pow(torch.tensor(10000.0, dtype=torch.float64),
-                    -torch.arange(half, dtype=torch.float64) / half)
+                    -torch.arange(half, dtype=torch.float64) / half).to(pos.device)
     ang = pos[:, None] * inv[None, :]
     return torch.cat([ang.cos(), ang.sin()], dim=1)
 
@@ -142,11 +148,12 @@ def rope_apply(x: torch.Tensor, grids: Sequence[Tuple[int, int, int]],
     for i, g in enumerate(grids):
         seq_len = g[0] * g[1] * g[2]
         cos, sin = rope_table(g, d)
+        cos, sin = cos.to(x.device), sin.to(x.device)
         if sp_size > 1:
             total = s * sp_size
             if total > seq_len:  # pad_freqs: multiply by 1+0j
-                cos = torch.cat([cos, torch.ones(total - seq_len, d // 2, dtype=cos.dtype)])
-                sin = torch.cat([sin, torch.zeros(total - seq_len, d // 2, dtype=sin.dtype)])
+                cos = torch.cat([cos, torch.ones(total - seq_len, d // 2, dtype=cos.dtype, device=cos.device)])
+                sin = torch.cat([sin, torch.zeros(total - seq_len, d // 2, dtype=sin.dtype, device=sin.device)])
             cos = cos[sp_rank * s:(sp_rank + 1) * s]
             sin = sin[sp_rank * s:(sp_rank + 1) * s]
             nrot = s
@@ -191,6 +198,9 @@ def flash_attention(q, k, v, prec: _Prec, k_len: Optional[int] = None) -> torch.
     qh, kh, vh = prec.half(q), prec.half(k), prec.half(v)
     if k_len is not None:
         kh, vh = kh[:, :k_len], vh[:, :k_len]
+    if prec.native and qh.is_cuda:
+        from flash_attn import flash_attn_func                # attention.py:113-127 (FA2), [B, L, N, d] layout
+        return flash_attn_func(qh.contiguous(), kh.contiguous(), vh.contiguous()).to(out_dtype)
     o = F.scaled_dot_product_attention(qh.float().transpose(1, 2), kh.float().transpose(1, 2),
                                        vh.float().transpose(1, 2))
     o = o.transpose(1, 2)
@@ -347,12 +357,12 @@ def wan_forward(sd: Dict[str, torch.Tensor], cfg: WanConfig, x: List[torch.Tenso
                 context: List[torch.Tensor], seq_len: int, clip_fea=None, y=None,
                 output_features: bool = False, selected_layers: Sequence[int] = (20, 30, 40),
                 autocast_dtype: Optional[torch.dtype] = None, num_blocks: Optional[int] = None,
-                sp_size: int = 1, return_block_outputs: bool = False):
+                sp_size: int = 1, return_block_outputs: bool = False, native: bool = False):
     """WanModel.forward (model.py:534-681).  With sp_size > 1 the P sequence-parallel ranks are
     emulated in this one process: tokens are chunked (model.py:618-619), the Ulysses exchanges
     of model.py:183-196 are performed on the list of per-rank tensors, and features / head output
     are concatenated (all_gather, model.py:663-664,675-676)."""
-    prec = _Prec(autocast_dtype)
+    prec = _Prec(autocast_dtype, native)
     if cfg.model_type in ("i2v", "flf2v"):
         assert clip_fea is not None and y is not None
     if y is not None:
@@ -454,12 +464,12 @@ def _sp_block(sd, pfx, shards, e0, grids, seq_lens, ctx, cfg, prec):
 # PAVRM reward head   (network.py:8-152)
 # ----------------------------------------------------------------------------------------------
 def query_attention(sd: Dict[str, torch.Tensor], x: torch.Tensor, num_heads: int = 8,
-                    return_type: Optional[str] = "query", autocast_dtype=None) -> torch.Tensor:
+                    return_type: Optional[str] = "query", autocast_dtype=None, native: bool = False) -> torch.Tensor:
     """QueryAttention.forward (network.py:44-110) for layer_norm=False, product_text=False, eval
     mode (dropout inactive).  x: [n_sel, B, L, C] | [B, L, C] | [B, C].  nn.MultiheadAttention
     semantics: q = queries Wq^T + bq, k = x Wk^T + bk, v = x Wv^T + bv (packed in_proj), per-head
     softmax(q k^T / sqrt(hd)) v, out_proj."""
-    prec = _Prec(autocast_dtype)
+    prec = _Prec(autocast_dtype, native)
     shape = x.shape
     if x.dim() == 2:
         x = x.unsqueeze(1)
@@ -489,9 +499,9 @@ def query_attention(sd: Dict[str, torch.Tensor], x: torch.Tensor, num_heads: int
     return out
 
 
-def reward_mlp(sd: Dict[str, torch.Tensor], x: torch.Tensor, autocast_dtype=None) -> torch.Tensor:
+def reward_mlp(sd: Dict[str, torch.Tensor], x: torch.Tensor, autocast_dtype=None, native: bool = False) -> torch.Tensor:
     """MLP.forward (network.py:130-134): the pre-sigmoid reward logit."""
-    prec = _Prec(autocast_dtype)
+    prec = _Prec(autocast_dtype, native)
     h = torch.relu(prec.linear(x, sd["fc1.weight"], sd["fc1.bias"]))
     h = torch.relu(prec.linear(h, sd["fc2.weight"], sd["fc2.bias"]))
     return prec.linear(h, sd["fc3.weight"], sd["fc3.bias"])
@@ -503,12 +513,12 @@ def forward_mlp(sd, x, autocast_dtype=None):
 
 
 def pavrm_reward(sd_model, cfg, sd_qa, sd_mlp, x, t, context, seq_len, clip_fea=None, y=None,
-                 selected_layers=(8,), num_blocks=8, qa_heads=8, autocast_dtype=None, sp_size=1):
+                 selected_layers=(8,), num_blocks=8, qa_heads=8, autocast_dtype=None, sp_size=1, native=False):
     """PAVRM scoring chain (train_pavrm.py:792-845, train_prfl.py:764-796): features of the
     selected block(s) -> list2batch -> QueryAttention -> MLP.  Returns (logit, features)."""
     feats = wan_forward(sd_model, cfg, x, t, context, seq_len, clip_fea, y, output_features=True,
                         selected_layers=selected_layers, autocast_dtype=autocast_dtype,
-                        num_blocks=num_blocks, sp_size=sp_size)
+                        num_blocks=num_blocks, sp_size=sp_size, native=native)
     stacked = torch.stack(feats)                                      # [n_sel, B, L, C]
-    pooled = query_attention(sd_qa, stacked, qa_heads, "query", autocast_dtype)
-    return reward_mlp(sd_mlp, pooled, autocast_dtype), stacked
+    pooled = query_attention(sd_qa, stacked, qa_heads, "query", autocast_dtype, native)
+    return reward_mlp(sd_mlp, pooled, autocast_dtype, native).float(), stacked

@@ -231,6 +231,25 @@ def case_unipc(name):
     print(name, "ok", {k: float(v["loss"]) for k, v in grads.items()})
 
 
+def case_unipc_fresh(name):
+    """add_noise on a FRESHLY CONSTRUCTED scheduler (no set_timesteps): its schedule is the float tensor
+    `sigmas * num_train_timesteps` (fm_solvers_unipc.py:96-103) whose entries share integer parts once shift > 1
+    squeezes them together near sigma ~ 1, so the lookup must compare exactly (fm_solvers_unipc.py:628-641)."""
+    S = ref_shim.load_scheduler()
+    g = torch.Generator().manual_seed(71)
+    fx = {"cases": {}}
+    for shift in (1.0, 5.0):
+        sch = S.FlowUniPCMultistepScheduler(num_train_timesteps=1000, shift=shift, use_dynamic_shifting=False)
+        idx = [0, 1, 2, 3, 10, 500, 998, 999]
+        ts = sch.timesteps[idx].clone()
+        clean = torch.randn(len(idx), 4, 1, 2, 3, generator=g)
+        eps = torch.randn(len(idx), 4, 1, 2, 3, generator=g)
+        fx["cases"][shift] = dict(idx=idx, timesteps=ts, schedule=sch.timesteps.clone(), clean=clean, eps=eps,
+                                  out=sch.add_noise(clean, eps, ts).clone())
+    torch.save(fx, os.path.join(HERE, name + ".pt"))
+    print(name, "ok", {k: int((v["schedule"].long().unique().numel())) for k, v in fx["cases"].items()}, "distinct integer parts of 1000")
+
+
 def case_checkpoint(name):
     """run the UNMODIFIED reference save_checkpoint (diffusers_lite/utils/model_utils.py:70-126) on the
     tiny T2V model and record what it wrote (directory name, file list, tensor keys, config.json).  Shims: `peft` (unused
@@ -280,10 +299,14 @@ if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "unipc":      # regenerate only the scheduler fixture
         case_unipc("unipc")
         sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "unipc_fresh":
+        case_unipc_fresh("unipc_fresh")
+        sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "checkpoint":
         case_checkpoint("checkpoint_ref")
         sys.exit(0)
     case_unipc("unipc")
+    case_unipc_fresh("unipc_fresh")
     case_checkpoint("checkpoint_ref")
     case_ops(M, "ops")
     case_model(M, "tiny_t2v", synth.tiny_cfg("t2v"), (5, 12, 20), 10, 11, [1, 2])

@@ -25,7 +25,7 @@ def test_header_symbols_exported():
     for n in names:
         assert hasattr(dll, n), f"{n} declared in include/prfl_b200.h but not exported"
     assert set(names) == set(_lib._SIGS), set(names) ^ set(_lib._SIGS)
-    assert _lib.lib().prfl_abi_version() == 1
+    assert _lib.lib().prfl_abi_version() == 2
 
 
 @pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU behaviour")

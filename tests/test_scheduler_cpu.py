@@ -162,3 +162,16 @@ def test_add_noise_matches_reference():
     s._step_index = 6                                        # the state after one step from begin index 5
     torch.testing.assert_close(s.add_noise(clean, eps, ts), fx["add_noise"]["after_step"], rtol=0, atol=0)
     assert len(s) == 1000 and s.scale_model_input(clean) is clean
+
+
+def test_add_noise_on_fresh_scheduler_float_schedule():
+    """A scheduler that never saw set_timesteps() has the float schedule `sigmas * 1000`; with shift = 5 many entries share
+    an integer part (golden from the unmodified reference: tests/golden/make_golden.py case_unipc_fresh)."""
+    from prfl_b200.scheduler import FlowUniPCMultistepScheduler
+    fx = golden("unipc_fresh")
+    for shift, c in fx["cases"].items():
+        s = FlowUniPCMultistepScheduler(num_train_timesteps=1000, shift=shift, use_dynamic_shifting=False)
+        assert torch.equal(s.timesteps, c["schedule"])
+        for i, t in zip(c["idx"], c["timesteps"]):
+            assert s.index_for_timestep(t, s.timesteps) == i
+        torch.testing.assert_close(s.add_noise(c["clean"], c["eps"], c["timesteps"]), c["out"], rtol=0, atol=0)

@@ -1,0 +1,129 @@
+"""GPU (1 device): the resident-bf16 training layout of prfl_b200.sharding against the replicated
+fp32 layout it replaces — same kernels, so forwards must be bit-identical and the optimizer trajectories must agree to
+rounding:
+  * `make_resident` / `ShardedAdamW(resident)` re-point the block matrices to views of a flat bf16 buffer: forward equals
+    the fp32-parameter model's forward exactly (both feed bf16(weight) to the GEMMs);
+  * weight gradients written through the gradient sink equal the autograd-returned ones bit for bit, including fused
+    QKV / context-KV operands and accumulation over two backward() calls;
+  * two optimizer steps (clip 1.0) match dense torch.optim.AdamW on the fp32 model: masters to 1e-4 per tensor;
+  * full_state_dict() returns fp32 masters under the reference's key names; frozen resident models (PRFL's reward
+    transformer) back-propagate to their input without weight gradients.
+"""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _models(mt="t2v", seed=60):
+    from oracle import synth
+    from prfl_b200.model import WanModel
+    cfg = synth.tiny_cfg(mt, heads=2, layers=2)
+    sd = synth.make_wan_state_dict(cfg, seed)
+    g = torch.Generator().manual_seed(seed + 1)
+    sd["head.head.weight"] = torch.randn(sd["head.head.weight"].shape, generator=g) * 0.02
+    inp = synth.make_inputs(cfg, (3, 8, 12), seed + 2)
+
+    def make():
+        m = WanModel(**cfg.kwargs())
+        m.load_state_dict(sd, strict=True)
+        return m.cuda().train()
+    kw = dict(t=inp["t"].cuda(), context=[c.cuda() for c in inp["context"]], seq_len=inp["seq_len"])
+    if mt == "i2v":
+        kw.update(clip_fea=inp["clip_fea"].cuda(), y=[u.cuda() for u in inp["y"]])
+    return cfg, sd, inp, make, kw
+
+
+@pytest.mark.parametrize("mt", ["t2v", "i2v"])
+def test_resident_forward_bit_identical_and_sink_grads_equal(mt):
+    from prfl_b200.sharding import ShardedAdamW
+    cfg, sd, inp, make, kw = _models(mt)
+    a, b = make(), make()
+    opt = ShardedAdamW(a, lr=1e-3).attach_hooks()
+    assert opt.resident and a.blocks[0].self_attn.q.weight.dtype == torch.bfloat16
+    # fused operands are views of the resident buffer, not copies
+    wqkv, _ = a.blocks[0].self_attn._qkv_operands()
+    assert wqkv.data_ptr() == a.blocks[0].self_attn.q.weight.data_ptr() and wqkv.shape == (3 * cfg.dim, cfg.dim)
+    x = [u.cuda() for u in inp["x"]]
+    with torch.no_grad():
+        assert torch.equal(a(x=x, **kw)[0], b(x=x, **kw)[0])
+    g = torch.Generator().manual_seed(5)
+    for micro in range(2):                                          # two backward() calls accumulate
+        cot = torch.randn(a(x=x, **kw)[0].shape, generator=g).cuda()
+        (a(x=x, **kw)[0] * cot).sum().backward()
+        (b(x=x, **kw)[0] * cot).sum().backward()
+    shards = opt.reduce_gradients()
+    names = dict(b.named_parameters())
+    for ui, u in enumerate(opt.units):
+        for n, (o, cnt, shp) in u.offsets.items():
+            full = (u.sink.prefix + n) if u.kind == "resident" else n
+            want = names[full].grad
+            got = shards[ui][o:o + cnt].view(shp)
+            if want is None:
+                assert float(got.abs().max()) == 0.0, full
+            else:
+                assert torch.equal(got, want.float()), full
+    assert all(p.grad is None for p in a.parameters())
+
+
+def test_sharded_adamw_resident_matches_dense_adamw():
+    from prfl_b200.sharding import ShardedAdamW
+    cfg, sd, inp, make, kw = _models("t2v", 70)
+    a, b = make(), make()
+    opt_a = ShardedAdamW(a, lr=1e-3, weight_decay=0.01).attach_hooks()
+    opt_b = torch.optim.AdamW(b.parameters(), lr=1e-3, weight_decay=0.01)
+    for step in range(2):
+        g = torch.Generator().manual_seed(300 + step)
+        x = [torch.randn(inp["x"][0].shape, generator=g).cuda()]
+        cot = torch.randn(16, *inp["x"][0].shape[1:], generator=g).cuda()
+        (a(x=x, **kw)[0] * cot).sum().backward()
+        na = opt_a.step(max_norm=1.0)
+        (b(x=x, **kw)[0] * cot).sum().backward()
+        for p in b.parameters():
+            if p.grad is None:
+                p.grad = torch.zeros_like(p)
+        nb = torch.nn.utils.clip_grad_norm_(b.parameters(), 1.0)
+        opt_b.step()
+        opt_b.zero_grad(set_to_none=True)
+        assert abs(float(na) - float(nb)) <= 1e-4 * float(nb)
+    full = opt_a.full_state_dict()
+    assert set(full) == set(b.state_dict())
+    for k, v in b.state_dict().items():
+        assert full[k].dtype == torch.float32 or "freqs" in k
+        d = float((full[k].float() - v.float().cpu()).abs().max() / (v.float().abs().max().cpu() + 1e-12))
+        assert d <= 1e-4, (k, d)
+    # the resident bf16 copy is bf16(master)
+    u = opt_a.units[0]
+    assert torch.equal(u.wflat[:u.n].float(), u.master[:u.n].bfloat16().float())
+    with torch.no_grad():
+        oa, ob = a(x=x, **kw)[0], b(x=x, **kw)[0]
+    assert float((oa - ob).abs().max() / ob.abs().max()) <= 1e-3
+
+
+def test_frozen_resident_model_backpropagates_to_input_only():
+    from prfl_b200.sharding import make_resident
+    cfg, sd, inp, make, kw = _models("t2v", 80)
+    a, b = make(), make()
+    for m in (a, b):
+        for p in m.parameters():
+            p.requires_grad_(False)
+    make_resident(a)
+    x1 = [inp["x"][0].cuda().requires_grad_(True)]
+    x2 = [inp["x"][0].cuda().requires_grad_(True)]
+    fa = a(x=x1, output_features=True, selected_layers=[2], **kw)[0]
+    fb = b(x=x2, output_features=True, selected_layers=[2], **kw)[0]
+    assert torch.equal(fa, fb)
+    fa.square().sum().backward()
+    fb.square().sum().backward()
+    assert torch.equal(x1[0].grad, x2[0].grad)
+    assert a.blocks[0].ffn[0].weight.dtype == torch.bfloat16 and a.blocks[0].ffn[0].weight.grad is None
+
+
+def test_resident_block_without_optimizer_refuses_weight_grads():
+    from prfl_b200.sharding import make_resident
+    cfg, sd, inp, make, kw = _models("t2v", 90)
+    a = make()
+    make_resident(a, trainable=True)
+    out = a(x=[u.cuda() for u in inp["x"]], **kw)[0]
+    with pytest.raises(RuntimeError, match="gradient sink|ShardedAdamW"):
+        out.sum().backward()
