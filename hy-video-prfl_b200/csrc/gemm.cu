@@ -404,7 +404,14 @@ extern "C" int prfl_gemm_bf16(const void* A, int64_t lda, int a_trans, const voi
     const char* e = getenv("PRFL_GEMM_GROUP_M");
     return e ? atoi(e) : 0;
   }();
-  p.group_m = group_env != 0 ? group_env : 8;
+  // Raster default, from the round-2 sweep on B200 (profiles/r02_gemm_raster.md; 14B block shapes at M = 32 760, same box,
+  // CUDA events): row-tile groups of 16 when a group's A panels fit L2 comfortably (K <= 8192: QKV +1 %, ffn.0 +6 %) and for
+  // the wgrad shapes (+13 %); column-tile groups of 8 when N is short (o-proj + gated residual: 1 042 -> 1 185 TFLOP/s,
+  // the fp32 read-modify-write of a row stays in one DRAM page); row-tile groups of 8 for long K (ffn.2, dgrad).
+  int group_auto = 8;
+  if (a_trans && b_trans) group_auto = 16;
+  else if (K <= 8192) group_auto = p.tiles_n <= 24 ? -8 : 16;
+  p.group_m = group_env != 0 ? group_env : group_auto;
   cudaStream_t st = (cudaStream_t)stream;
   if (cg == 2) {
     if (!a_trans && !b_trans) return launch_gemm<false, false, 2>(tmA, tmB, p, st);

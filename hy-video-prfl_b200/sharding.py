@@ -322,8 +322,9 @@ class ShardedAdamW:
     @staticmethod
     def _make_hook(u: FlatUnit):
         def hook(p):
-            u.add_grad(id(p), p.grad)
-            p.grad = None
+            if p.grad is not None:          # the hook also fires when a Function returned None for this input (gradient sink)
+                u.add_grad(id(p), p.grad)
+                p.grad = None
         return hook
 
     # staging buffers for resident units (two, shared): wgrad GEMMs of unit i write one while unit i+1's is in flight

@@ -200,6 +200,11 @@ def test_sample_loop_vs_oracle_and_context_cache_is_exact(mt):
     traj = []
     out = sample_loop(model, noise.cuda(), ctx, ctx_null, inp["seq_len"], sampling_steps=steps, shift=shift, guide_scale=g,
                       clip_fea=clip, y=y, trajectory=traj)[0]
+    # batching cond + uncond as one B = 2 forward (default) is bit-identical to the two sequential forwards
+    traj_seq = []
+    out_seq = sample_loop(model, noise.cuda(), ctx, ctx_null, inp["seq_len"], sampling_steps=steps, shift=shift, guide_scale=g,
+                          clip_fea=clip, y=y, trajectory=traj_seq, batch_cfg=False)[0]
+    assert torch.equal(out, out_seq) and all(torch.equal(a, b) for a, b in zip(traj, traj_seq))
     # (a) the reference's own loop structure over the same modules
     sch = FlowUniPCMultistepScheduler(num_train_timesteps=1000, shift=1, use_dynamic_shifting=False)
     sch.set_timesteps(steps, device="cuda", shift=shift)

@@ -77,6 +77,28 @@ def main():
         del q, k, v, do, o, lse, dq, dk, dv
         torch.cuda.empty_cache()
 
+    # cross-attention shapes (short KV: 512 T5 tokens / 257 CLIP tokens, model.py:206-226, 244-271)
+    if "cross" in sections:
+        res["cross_attention"] = []
+        for Lq in ([32760] if args.quick else [32760, 75600]):
+            for Lk in (512, 257):
+                q = torch.randn(Lq, H, 128, generator=g, device="cuda").bfloat16()
+                k, v = (torch.randn(Lk, H, 128, generator=g, device="cuda").bfloat16() for _ in range(2))
+                do = torch.randn(Lq, H, 128, generator=g, device="cuda").bfloat16()
+                fl = 4.0 * Lq * Lk * 128 * H
+                t_f = timeit(lambda: ops.attn_fwd(q, k, v), 20)
+                o, lse = ops.attn_fwd(q, k, v, need_lse=True)
+                t_b = timeit(lambda: ops.attn_bwd(q, k, v, o, do, lse), 10)
+                row = {"Lq": Lq, "Lk": Lk, "heads": H, "fwd_ms": t_f, "fwd_tflops": fl / t_f / 1e9, "bwd_ms": t_b,
+                       "bwd_tflops_algorithmic": 2.5 * fl / t_b / 1e9,
+                       "io_bytes_fwd": 2.0 * (2 * Lq + 2 * Lk) * H * 128, "fwd_GBps": 2.0 * (2 * Lq + 2 * Lk) * H * 128 / t_f / 1e6}
+                if flash_attn_func is not None:
+                    t_ff = timeit(lambda: flash_attn_func(q[None], k[None], v[None]), 20)
+                    row.update({"fa2_fwd_ms": t_ff, "speedup_fwd_vs_fa2": t_ff / t_f})
+                res["cross_attention"].append(row)
+                print(json.dumps(row), file=sys.stderr)
+                del q, k, v, do, o, lse
+
     # memory-bound kernels at the 480P token count
     M, C = 32760, 5120
     if "membound" not in sections:
