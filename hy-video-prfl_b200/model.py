@@ -549,23 +549,41 @@ class WanModel(nn.Module):
         dev = self.patch_embedding.weight.device
         wp, bp = self._patch_operands()
         train = torch.is_grad_enabled() and (any(p.requires_grad for p in self.parameters()) or any(u.requires_grad for u in x))
-        embs, grids = [], []
+        sp_on = get_sequence_parallel_state()
+        sp_P = nccl_info.sp_size if sp_on else 1
+        sp_r = nccl_info.rank_within_group if sp_on else 0
+        local_only = sp_on and not train                 # no-grad under Ulysses: embed only this rank's token chunk
+        if local_only:
+            assert seq_len % sp_P == 0
+            M_loc = seq_len // sp_P
+            xs = torch.empty(len(x), M_loc, self.dim, dtype=torch.float32, device=dev)
+        embs, grids, lens = [], [], []
         for i, u in enumerate(x):
             yi = None if y is None else y[i].to(device=dev)
+            grids.append((u.shape[1] // self.patch_size[0], u.shape[2] // self.patch_size[1], u.shape[3] // self.patch_size[2]))
+            lens.append(grids[-1][0] * grids[-1][1] * grids[-1][2])
             if train:
                 from .engine import PatchEmbedFn
                 embs.append(PatchEmbedFn.apply(u.to(dev), yi, self.patch_embedding.weight, self.patch_embedding.bias, self))
             else:
                 yf = None if yi is None else yi.to(torch.float32).contiguous()
                 patches = ops.patchify(u.to(device=dev, dtype=torch.float32).contiguous(), yf)
-                embs.append(ops.gemm(patches, wp, bias=bp, epi=ops.EPI_BF16))        # [L_i, dim] bf16, like the autocast conv
-            grids.append((u.shape[1] // self.patch_size[0], u.shape[2] // self.patch_size[1], u.shape[3] // self.patch_size[2]))
-        seq_lens = torch.tensor([e_.size(0) for e_ in embs], dtype=torch.long)
+                if local_only:
+                    # rows [r*M, (r+1)*M) of the padded sequence: the patch-embedding GEMM and the fp32 stream exist only for
+                    # them (the reference embeds and zero-fills all L tokens on every rank, then chunks: model.py:578-619)
+                    lo, hi = sp_r * M_loc, min((sp_r + 1) * M_loc, lens[-1])
+                    if hi > lo:
+                        xs[i, :hi - lo] = ops.gemm(patches[lo:hi], wp, bias=bp, epi=ops.EPI_BF16)
+                    if hi - lo < M_loc:
+                        xs[i, max(hi - lo, 0):].zero_()
+                else:
+                    embs.append(ops.gemm(patches, wp, bias=bp, epi=ops.EPI_BF16))    # [L_i, dim] bf16, like the autocast conv
+        seq_lens = torch.tensor(lens, dtype=torch.long)
         grid_sizes = torch.tensor(grids, dtype=torch.long)
         assert int(seq_lens.max()) <= seq_len
         if train:
             xs = torch.stack([torch.cat([e_.float(), e_.new_zeros(seq_len - e_.size(0), self.dim, dtype=torch.float32)]) for e_ in embs])
-        else:
+        elif not local_only:
             xs = torch.zeros(len(embs), seq_len, self.dim, dtype=torch.float32, device=dev)
             for i, e_ in enumerate(embs):
                 xs[i, :e_.size(0)] = e_
@@ -584,7 +602,7 @@ class WanModel(nn.Module):
                                "only, or pass the raw context when those weights are being trained")
         ctx = prepared.embedded if prepared is not None else self._embed_context(context, clip_fea)
 
-        if get_sequence_parallel_state():
+        if sp_on and not local_only:
             xs = torch.chunk(xs, nccl_info.sp_size, dim=1)[nccl_info.rank_within_group].contiguous()
 
         features_list = []

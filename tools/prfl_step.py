@@ -33,7 +33,7 @@ def algorithmic_flops(L: int, i2v: bool, world: int):
     return (lin + att) / world, (2 * lin + 2.5 * att) / world
 
 
-def fit_blocks(world: int, L: int, want: int = 40, budget_gb: float = 150.0) -> int:
+def fit_blocks(world: int, L: int, want: int = 40, budget_gb: float = 138.0) -> int:
     """Largest VGM depth (<= want) whose training state fits `budget_gb` per GPU: bf16 resident weights + 1/W fp32
     master / moment shards + the per-block saved fp32 inputs (activation checkpointing) + one block's recompute stash."""
     per_block_params = 351.4e6 + 52.4e6
