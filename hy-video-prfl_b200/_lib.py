@@ -35,6 +35,7 @@ _SIGS = {
     "prfl_attn_fwd_ws_bytes": (_i64, [_i32, _i32, _i32]),
     "prfl_attn_fwd_split_plan": (None, [_i32, _i32, _i32, _i32, _p]),
     "prfl_attn_fwd": (C.c_int, [_p, _i64, _i64, _p, _i64, _i64, _p, _i64, _i64, _p, _i64, _i64, _p, _i32, _i32, _i32, _f32, _p, _p]),
+    "prfl_attn_merge": (C.c_int, [_p, _p, _p, _i64, _i64, _p, _i32, _p, _i64, _i64, _i32, _i32, _p]),
     "prfl_colsum_parts": (C.c_int, [_i64]),
     "prfl_ln_mod_bwd": (C.c_int, [_p, _p, _p, _p, _p, _p, _p, _p, _p, _i64, _i32, _p]),
     "prfl_rmsnorm_rope_bwd": (C.c_int, [_p, _i64, _p, _p, _p, _p, _i64, _p, _p, _i64, _p, _i64, _i64, _i32, _i64, _i64, _p]),

@@ -392,9 +392,65 @@ __global__ void __launch_bounds__(256) attn_combine_kernel(const AttnFwdParams p
   if (lane == 0 && p.lse) p.lse[(int64_t)head * p.Lq + row] = (m + log2f(den)) * 0.6931471805599453f;
 }
 
+// Ring / context-parallel merge (xdit_context_parallel.py:190-233 + xfuser's ring attention): combine the
+// running result over the key blocks seen so far with the attention over one more key block.  One warp per (token, head),
+// lane = 4 output columns.  LSEs in natural log (what prfl_attn_fwd writes).
+//   m = max(lse_a, lse_n); w_a = e^(lse_a - m), w_n = e^(lse_n - m); acc = (w_a acc + w_n o_n) / (w_a + w_n); lse_a = m + ln(w_a + w_n)
+__global__ void __launch_bounds__(256) attn_merge_kernel(float* __restrict__ acc, float* __restrict__ lse_acc,
+                                                         const __nv_bfloat16* __restrict__ o_new, int64_t n_ld_tok, int64_t n_ld_head,
+                                                         const float* __restrict__ lse_new, int first,
+                                                         __nv_bfloat16* __restrict__ out, int64_t o_ld_tok, int64_t o_ld_head, int L, int H) {
+  const int lane = threadIdx.x & 31;
+  const int64_t w = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (w >= (int64_t)L * H) return;
+  const int h = (int)(w % H);
+  const int64_t i = w / H;
+  const uint2 nv = *reinterpret_cast<const uint2*>(o_new + i * n_ld_tok + (int64_t)h * n_ld_head + lane * 4);
+  float4 r = make_float4(bf16lo(nv.x), bf16hi(nv.x), bf16lo(nv.y), bf16hi(nv.y));
+  float* a = acc + (i * H + h) * HD + lane * 4;
+  const float ln = lse_new[(int64_t)h * L + i];
+  float lse = ln;
+  if (!first) {
+    const float la = lse_acc[(int64_t)h * L + i];
+    const float m = fmaxf(la, ln);
+    const float wa = __expf(la - m), wn = __expf(ln - m);
+    const float inv = 1.0f / (wa + wn);
+    const float4 av = *reinterpret_cast<const float4*>(a);
+    r.x = (wa * av.x + wn * r.x) * inv; r.y = (wa * av.y + wn * r.y) * inv;
+    r.z = (wa * av.z + wn * r.z) * inv; r.w = (wa * av.w + wn * r.w) * inv;
+    lse = m + __logf(wa + wn);
+  }
+  *reinterpret_cast<float4*>(a) = r;
+  if (lane == 0) lse_acc[(int64_t)h * L + i] = lse;
+  if (out) {
+    uint2 o;
+    o.x = pack_bf16x2(r.x, r.y);
+    o.y = pack_bf16x2(r.z, r.w);
+    *reinterpret_cast<uint2*>(out + i * o_ld_tok + (int64_t)h * o_ld_head + lane * 4) = o;
+  }
+}
+
 }  // namespace prfl
 
 using namespace prfl;
+
+extern "C" int prfl_attn_merge(float* o_acc, float* lse_acc, const void* o_new_bf16, int64_t n_ld_tok, int64_t n_ld_head,
+                               const float* lse_new, int first, void* out_bf16, int64_t o_ld_tok, int64_t o_ld_head, int L, int H,
+                               prfl_stream_t stream) {
+  PRFL_CHECK_ARCH();
+  PRFL_REQUIRE(L > 0 && H > 0 && o_acc && lse_acc && o_new_bf16 && lse_new, PRFL_E_SHAPE, "attn_merge: L=%d H=%d", L, H);
+  PRFL_REQUIRE(n_ld_tok % 4 == 0 && n_ld_head % 4 == 0 && o_ld_tok % 4 == 0 && o_ld_head % 4 == 0 &&
+                   (reinterpret_cast<uintptr_t>(o_acc) & 15) == 0 && (reinterpret_cast<uintptr_t>(o_new_bf16) & 7) == 0 &&
+                   (reinterpret_cast<uintptr_t>(out_bf16) & 7) == 0,
+               PRFL_E_ALIGN, "attn_merge: alignment");
+  const int64_t warps = (int64_t)L * H;
+  attn_merge_kernel<<<(unsigned)((warps + 7) / 8), 256, 0, (cudaStream_t)stream>>>(
+      o_acc, lse_acc, (const __nv_bfloat16*)o_new_bf16, n_ld_tok, n_ld_head, lse_new, first, (__nv_bfloat16*)out_bf16, o_ld_tok,
+      o_ld_head, L, H);
+  count_launch();
+  PRFL_LAUNCH_CHECK("attn_merge");
+  return PRFL_OK;
+}
 
 // Tail plan: units beyond the last full wave are split `n_split` ways along the key axis when that shortens the kernel.
 struct SplitPlan {

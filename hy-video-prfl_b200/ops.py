@@ -208,6 +208,26 @@ def attn_bwd(q, k, v, o, dout, lse, dq=None, dk=None, dv=None, scale: Optional[f
     return dq, dk, dv
 
 
+def attn_merge_(o_acc: torch.Tensor, lse_acc: torch.Tensor, o_new: torch.Tensor, lse_new: torch.Tensor, first: bool,
+                out: Optional[torch.Tensor] = None):
+    """Ring-attention merge: fold (o_new bf16 [L, H, 128] view, lse_new [H, L]) into the running fp32 (o_acc [L, H, 128]
+    contiguous, lse_acc [H, L]); `out` (bf16 [L, H, 128] view) also receives bf16(o_acc)."""
+    _req(o_acc, f32, "attn_merge.o_acc")
+    _req(lse_acc, f32, "attn_merge.lse_acc")
+    _req(o_new, bf16, "attn_merge.o_new")
+    _req(lse_new, f32, "attn_merge.lse_new")
+    L, H, d = o_new.shape
+    assert d == 128 and o_new.stride(2) == 1 and o_acc.is_contiguous() and o_acc.shape == (L, H, 128)
+    assert lse_acc.shape == (H, L) and lse_new.shape == (H, L) and lse_acc.is_contiguous() and lse_new.is_contiguous()
+    if out is not None:
+        _req(out, bf16, "attn_merge.out")
+        assert out.shape == (L, H, 128) and out.stride(2) == 1
+    check(lib().prfl_attn_merge(_p(o_acc), _p(lse_acc), _p(o_new), o_new.stride(0), o_new.stride(1), _p(lse_new), int(first),
+                                _p(out), 0 if out is None else out.stride(0), 0 if out is None else out.stride(1), L, H, _stream()),
+          "prfl_attn_merge")
+    return o_acc
+
+
 def colsum_parts(rows: int) -> int:
     return (rows + 255) // 256
 
@@ -469,7 +489,7 @@ def sumsq_(x, acc):
 NVTX_FAMILIES = {
     "norm": ("ln_mod", "ln_mod_split", "rmsnorm_rope_", "ln_mod_bwd", "rmsnorm_rope_bwd_", "colsum", "gate_bwd", "cast_bf16"),
     "gemm": ("gemm",),
-    "attention": ("attn_fwd", "attn_bwd", "attn_fwd_p2p"),
+    "attention": ("attn_fwd", "attn_bwd", "attn_fwd_p2p", "attn_merge_"),
     "exchange": ("a2a_pack", "a2a_scatter_p2p"),
     "patch": ("patchify", "patchify_bwd", "unpatchify", "unpatchify_bwd"),
     "reward": ("sq_pool", "sq_pool_bwd"),

@@ -193,6 +193,16 @@ int prfl_sq_pool_bwd(const float* x, const float* wk_eff, const float* scores, c
                      const float* pooled, const float* dpooled, float* dx, float* ds, int64_t L, int C, int NH,
                      int accumulate, prfl_stream_t stream);
 
+/* ---- ring / context-parallel attention merge ----------------------------------------------------
+ * Replaces the out/lse update of xfuser's ring attention behind xFuserLongContextAttention
+ * (diffusers_lite/wan/distributed/xdit_context_parallel.py:214-219): folds the attention over one more key block
+ * (o_new bf16 [L, H, 128] strided, lse_new [H, L] natural log, both from prfl_attn_fwd) into the running fp32 result
+ * (o_acc [L, H, 128] contiguous, lse_acc [H, L]).  first != 0 initialises the running result.  out_bf16 (may be NULL):
+ * strided [L, H, 128] destination that also receives bf16(o_acc) — pass it on the last block. */
+int prfl_attn_merge(float* o_acc, float* lse_acc, const void* o_new_bf16, int64_t n_ld_tok, int64_t n_ld_head,
+                    const float* lse_new, int first, void* out_bf16, int64_t o_ld_tok, int64_t o_ld_head, int L, int H,
+                    prfl_stream_t stream);
+
 /* ---- misc elementwise --------------------------------------------------------------------------*/
 /* dst_bf16[i] = bf16(src_f32[i]) — fp32 master weights -> bf16 operands (what autocast does per call,
  * done once here). n % 8 == 0 not required. */

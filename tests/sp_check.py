@@ -9,9 +9,9 @@ Checks, on every rank:
                 the oracle's SP=1 gradient, same tolerances
   sharded_adamw `ShardedAdamW` (resident bf16 weights, reduce-scattered fp32 gradient shards, 1/W fp32 masters,
                 bf16 all-gather) vs dense torch.optim.AdamW on all-reduced(AVG) gradients of the replicated fp32 model,
-                2 steps with clip_grad_norm_(1.0): fp32 masters agree to max-rel <= 1e-4 per tensor (a layout / collective
-                bug shows up at >= 1e-2: one Adam step moves a weight by lr = 1e-3; the slack covers a bf16 ulp flip
-                of a resident weight after step 1) and the two models' forward outputs stay equal
+                2 steps with clip_grad_norm_(1.0), the dense model re-synchronised to the sharded masters in between:
+                fp32 masters agree to max-rel <= 1e-5 per tensor after each step (a layout / collective bug shows up at
+                >= 1e-2: one Adam step moves a weight by lr = 1e-3) and the two models' forward outputs stay equal
 """
 import os
 import sys
@@ -26,7 +26,7 @@ from conftest import cos_rel  # noqa: E402
 from oracle import synth  # noqa: E402
 from oracle import wan_oracle as O  # noqa: E402
 
-COS_MIN, REL_MAX, LOGIT_TOL, ADAMW_REL = 0.999, 2e-2, 1e-2, 1e-4
+COS_MIN, REL_MAX, LOGIT_TOL, ADAMW_REL = 0.999, 2e-2, 1e-2, 1e-5
 
 
 def run_checks(world: int, rank: int, verbose: bool = True) -> dict:
@@ -117,6 +117,7 @@ def run_checks(world: int, rank: int, verbose: bool = True) -> dict:
     opt_a = ShardedAdamW(a, lr=1e-3, weight_decay=0.01).attach_hooks()                  # resident bf16 + sharded state (auto)
     assert opt_a.resident
     opt_b = torch.optim.AdamW(b.parameters(), lr=1e-3, weight_decay=0.01)
+    worst = 0.0
     for step in range(2):
         gi = torch.Generator().manual_seed(200 + step)
         xin = [torch.randn(inp["x"][0].shape, generator=gi).to(dev)]
@@ -131,11 +132,13 @@ def run_checks(world: int, rank: int, verbose: bool = True) -> dict:
         torch.nn.utils.clip_grad_norm_(b.parameters(), 1.0)
         opt_b.step()
         opt_b.zero_grad(set_to_none=True)
-    full = opt_a.full_state_dict(to_cpu=True)
-    worst = 0.0
-    for k, v in b.state_dict().items():
-        d = float((full[k].float() - v.detach().float().cpu()).abs().max() / (v.detach().float().abs().max().cpu() + 1e-12))
-        worst = max(worst, d)
+        full = opt_a.full_state_dict(to_cpu=True)
+        for k, v in b.state_dict().items():
+            d = float((full[k].float() - v.detach().float().cpu()).abs().max() / (v.detach().float().abs().max().cpu() + 1e-12))
+            worst = max(worst, d)
+        # re-synchronise the dense model to the sharded masters (see tests/test_sharding_gpu.py: Adam amplifies the
+        # noise-dominated cross-attention gradients of this tiny model; with identical weights step 2 is as strict as step 1)
+        b.load_state_dict({k: v.to(dev) for k, v in full.items()}, strict=True)
     with torch.no_grad():
         oa = a(x=xin, t=inp["t"].to(dev), context=ctx, seq_len=inp["seq_len"])[0]
         ob = b(x=xin, t=inp["t"].to(dev), context=ctx, seq_len=inp["seq_len"])[0]

@@ -60,7 +60,7 @@ def test_install_runs_b200_kernels_on_shared_parameters(mt):
     assert _lib.launch_count() > 20                                     # the B200 kernels ran
     cos, rel = cos_rel(got.cpu(), want.cpu())
     assert cos >= 0.999 and rel <= 2e-2, (cos, rel)
-    assert ref.blocks[0]._prfl_b200_fast.ffn[0].weight is ref.blocks[0].ffn[0].weight
+    assert ref.blocks[0]._prfl_b200_fast.ffn[0].weight is ref.blocks[0].get_submodule("ffn.0").weight
     ref.prfl_b200_enable(False)
     with torch.no_grad():
         back = ref.blocks[1](ref.blocks[0](x, *args), *args)

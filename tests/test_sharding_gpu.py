@@ -85,19 +85,26 @@ def test_sharded_adamw_resident_matches_dense_adamw():
         nb = torch.nn.utils.clip_grad_norm_(b.parameters(), 1.0)
         opt_b.step()
         opt_b.zero_grad(set_to_none=True)
-        assert abs(float(na) - float(nb)) <= 1e-4 * float(nb)
-    full = opt_a.full_state_dict()
-    assert set(full) == set(b.state_dict())
-    for k, v in b.state_dict().items():
-        assert full[k].dtype == torch.float32 or "freqs" in k
-        d = float((full[k].float() - v.float().cpu()).abs().max() / (v.float().abs().max().cpu() + 1e-12))
-        assert d <= 1e-4, (k, d)
+        assert abs(float(na) - float(nb)) <= 1e-5 * float(nb)
+        full = opt_a.full_state_dict()
+        assert set(full) == set(b.state_dict())
+        for k, v in b.state_dict().items():
+            assert full[k].dtype == torch.float32
+            d = float((full[k].float() - v.float().cpu()).abs().max() / (v.float().abs().max().cpu() + 1e-12))
+            assert d <= 2e-6, (step, k, d)
+        # Re-synchronise the dense model to the sharded one's fp32 masters before the next step: Adam divides every
+        # element's update by its own gradient magnitude, so the 1e-7 rounding difference between the two AdamW
+        # implementations, through a bf16 ulp flip of a weight, turns the noise-dominated gradients of this model (the
+        # cross-attention q / k path over ~470 identical padded text tokens cancels almost exactly) into O(lr) weight
+        # differences at the following step.  With identical weights both sides compute bit-identical gradients again,
+        # so step 2 (non-zero moments, t = 2) is checked as strictly as step 1.
+        b.load_state_dict({k: v.cuda() for k, v in full.items()}, strict=True)
     # the resident bf16 copy is bf16(master)
     u = opt_a.units[0]
     assert torch.equal(u.wflat[:u.n].float(), u.master[:u.n].bfloat16().float())
     with torch.no_grad():
         oa, ob = a(x=x, **kw)[0], b(x=x, **kw)[0]
-    assert float((oa - ob).abs().max() / ob.abs().max()) <= 1e-3
+    assert torch.equal(oa, ob)                                      # same masters => same bf16 operands => same bits
 
 
 def test_frozen_resident_model_backpropagates_to_input_only():
