@@ -72,6 +72,13 @@ def block_forward(blk, x: torch.Tensor, em: torch.Tensor, ctx: torch.Tensor, seq
         else:
             a1 = ops.attn_fwd(q3, k3[:klen], v3[:klen])
         qg = kg = vg = og = None
+    elif nccl_info.ring_degree > 1:
+        # Ulysses x Ring (xdit_context_parallel.py:190-233): inference only in the reference, no-grad only here
+        if keep:
+            raise RuntimeError("Ulysses x Ring sequence parallelism is a no-grad (inference) path; train with ring_degree == 1")
+        from .parallel import usp_attention
+        a1 = usp_attention(q3, k3, v3, klen)
+        qg = kg = vg = og = None
     else:
         p2p = None if keep else get_p2p_ulysses(M * P, n, x.device)
         if p2p is not None:

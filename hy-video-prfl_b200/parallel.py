@@ -25,6 +25,14 @@ class COMM_INFO:
         self.global_rank = 0
         self.rank_within_group = 0
         self.group_id = 0
+        # Ulysses x Ring (USP): sp_size = ulysses_degree * ring_degree; ring_degree == 1 => plain Ulysses
+        self.ulysses_group = None
+        self.ring_group = None
+        self.ulysses_degree = 1
+        self.ring_degree = 1
+        self.ulysses_rank = 0
+        self.ring_rank = 0
+        self.ring_ranks = ()          # global ranks of this rank's ring, in ring order
 
 
 nccl_info = COMM_INFO()
@@ -44,6 +52,39 @@ def initialize_sequence_parallel_state(sequence_parallel_size: int):
         nccl_info.global_rank = int(os.getenv("RANK", "0"))
         nccl_info.rank_within_group = 0
         nccl_info.group_id = int(os.getenv("RANK", "0"))
+    nccl_info.ulysses_group, nccl_info.ring_group = nccl_info.group, None
+    nccl_info.ulysses_degree, nccl_info.ring_degree = nccl_info.sp_size, 1
+    nccl_info.ulysses_rank, nccl_info.ring_rank, nccl_info.ring_ranks = nccl_info.rank_within_group, 0, ()
+
+
+def initialize_usp_state(ulysses_degree: int, ring_degree: int):
+    """xfuser's unified sequence parallelism as the reference's inference entry point sets it up
+    (scripts/prfl/inference_prfl.py:71-82: `initialize_model_parallel(sequence_parallel_degree=world, ring_degree,
+    ulysses_degree)`): the sp group of U x R ranks holds U*R contiguous token chunks (chunk index = rank in the sp
+    group = ring_rank * U + ulysses_rank, xfuser's `use_ulysses_low` layout); Ulysses groups are the R runs of U
+    consecutive ranks, ring groups the U strided sets {u, u + U, ...}.  Inside self-attention (xdit_context_parallel.py:
+    190-233) an all-to-all over the Ulysses group turns [L/(UR), H] into [L/R, H/U], then the K/V blocks travel round
+    the ring while every rank attends its L/R queries to each block and merges the partial results by their LSEs."""
+    sp = ulysses_degree * ring_degree
+    initialize_sequence_parallel_state(sp)
+    nccl_info.ulysses_degree, nccl_info.ring_degree = ulysses_degree, ring_degree
+    nccl_info.ulysses_group, nccl_info.ring_group = nccl_info.group, None
+    nccl_info.ulysses_rank, nccl_info.ring_rank = nccl_info.rank_within_group, 0
+    if sp <= 1 or ring_degree == 1:
+        return
+    rank = dist.get_rank()
+    world = dist.get_world_size()
+    for base in range(0, world, sp):
+        for r in range(ring_degree):
+            ranks = [base + r * ulysses_degree + u for u in range(ulysses_degree)]
+            g = dist.new_group(ranks)
+            if rank in ranks:
+                nccl_info.ulysses_group, nccl_info.ulysses_rank = g, ranks.index(rank)
+        for u in range(ulysses_degree):
+            ranks = [base + u + r * ulysses_degree for r in range(ring_degree)]
+            g = dist.new_group(ranks)
+            if rank in ranks:
+                nccl_info.ring_group, nccl_info.ring_rank, nccl_info.ring_ranks = g, ranks.index(rank), tuple(ranks)
 
 
 def set_sequence_parallel_state(state: bool):
@@ -107,25 +148,94 @@ def _unpack_heads(packed: torch.Tensor, P: int, out: Optional[torch.Tensor] = No
     return res
 
 
-def _a2a(buf: torch.Tensor) -> torch.Tensor:
+def _a2a(buf: torch.Tensor, group=None) -> torch.Tensor:
     out = torch.empty_like(buf)
-    dist.all_to_all_single(out, buf, group=nccl_info.group)
+    dist.all_to_all_single(out, buf, group=nccl_info.group if group is None else group)
     return out
 
 
-def ulysses_scatter_tokens(x: torch.Tensor, P: int) -> torch.Tensor:
+def ulysses_scatter_tokens(x: torch.Tensor, P: int, group=None) -> torch.Tensor:
     """scatter heads / gather tokens: local [L/P, H, d] -> [L, H/P, d] (communication.py:60-89).
     The receive buffer [P, L/P, H/P, d] already is [L, H/P, d] in global token order."""
     L, H, d = x.shape
-    return _a2a(_pack_heads(x, P)).view(P * L, H // P, d)
+    return _a2a(_pack_heads(x, P), group).view(P * L, H // P, d)
 
 
-def ulysses_gather_tokens(x: torch.Tensor, P: int, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+def ulysses_gather_tokens(x: torch.Tensor, P: int, out: Optional[torch.Tensor] = None, group=None) -> torch.Tensor:
     """scatter tokens / gather heads: [L, H/P, d] -> local [L/P, H, d] (communication.py:91-123).
     The send buffer is x itself ([P, L/P, H/P, d] by token chunk).  `out`: optional strided destination view."""
     L, Hl, d = x.shape
-    recv = _a2a(x.contiguous().view(P, L // P, Hl, d))
+    recv = _a2a(x.contiguous().view(P, L // P, Hl, d), group)
     return _unpack_heads(recv, P, out)
+
+
+# ------------------------------------------------------------------------------------------------
+# Ulysses x Ring attention (no-grad; the reference uses it for inference only, text2video.py:137-148)
+# ------------------------------------------------------------------------------------------------
+def _merge_host(o_acc, lse_acc, o_new, lse_new, first):
+    """Host-logic twin of prfl_attn_merge for CPU tensors (gloo tests): same algebra in torch ops."""
+    if first:
+        o_acc.copy_(o_new.float())
+        lse_acc.copy_(lse_new)
+        return
+    m = torch.maximum(lse_acc, lse_new)
+    wa, wn = torch.exp(lse_acc - m), torch.exp(lse_new - m)
+    inv = 1.0 / (wa + wn)
+    o_acc.mul_((wa * inv).t().unsqueeze(-1)).add_(o_new.float() * (wn * inv).t().unsqueeze(-1))
+    lse_acc.copy_(m + torch.log(wa + wn))
+
+
+def usp_attention(q3: torch.Tensor, k3: torch.Tensor, v3: torch.Tensor, klen: int, attn_fn=None) -> torch.Tensor:
+    """Self-attention of one sample under Ulysses x Ring.  q3 / k3 / v3: this rank's [L/(UR), H, 128] bf16 token chunk
+    (q, k already normalised + rotated at their global positions); klen: number of valid keys of the sample.  Returns
+    this rank's [L/(UR), H, 128] attention output.
+
+      1. all-to-all over the Ulysses group: [L/(UR), H] -> [L/R, H/U]            (communication.py:60-89 on the sub-group)
+      2. R ring steps: attend the local L/R queries to the K/V block currently held (`prfl_attn_fwd` with LSE), fold it
+         into the running result (`prfl_attn_merge`), pass the block to the next rank of the ring while the attention
+         over it runs (isend / irecv on the ring group; blocks past `klen` are skipped, a partially valid block is cut)
+      3. all-to-all back: [L/R, H/U] -> [L/(UR), H]
+    `attn_fn(q, k, v) -> (o, lse)` is injectable for the CPU tests of the schedule; on the GPU it is ops.attn_fwd."""
+    U, R = nccl_info.ulysses_degree, nccl_info.ring_degree
+    rr = nccl_info.ring_rank
+    if attn_fn is None:
+        from . import ops
+        attn_fn = lambda q, k, v: ops.attn_fwd(q, k, v, need_lse=True)
+    ug = nccl_info.ulysses_group
+    qg, kg, vg = ((ulysses_scatter_tokens(t, U, ug) if U > 1 else t.contiguous()) for t in (q3, k3, v3))     # [L/R, H/U, d]
+    Lr, Hl, d = qg.shape
+    o_acc = torch.empty(Lr, Hl, d, dtype=torch.float32, device=qg.device)
+    lse_acc = torch.empty(Hl, Lr, dtype=torch.float32, device=qg.device)
+    out = torch.empty(Lr, Hl, d, dtype=qg.dtype, device=qg.device)
+    kv_cur = torch.stack([kg, vg])                                     # one message per ring step
+    nxt, prv = (nccl_info.ring_ranks[(rr + 1) % R], nccl_info.ring_ranks[(rr - 1) % R]) if R > 1 else (None, None)
+    first = True
+    for s in range(R):
+        reqs, kv_next = [], None
+        if s + 1 < R:
+            kv_next = torch.empty_like(kv_cur)
+            ops_ = [dist.P2POp(dist.isend, kv_cur, nxt, group=nccl_info.ring_group),
+                    dist.P2POp(dist.irecv, kv_next, prv, group=nccl_info.ring_group)]
+            reqs = dist.batch_isend_irecv(ops_)
+        blk = (rr - s) % R                                            # which token block the held K/V belongs to
+        valid = min(max(klen - blk * Lr, 0), Lr)
+        if valid > 0:
+            o_s, lse_s = attn_fn(qg, kv_cur[0][:valid], kv_cur[1][:valid])
+            last = all(min(max(klen - ((rr - t) % R) * Lr, 0), Lr) == 0 for t in range(s + 1, R))
+            if qg.is_cuda:
+                from . import ops
+                ops.attn_merge_(o_acc, lse_acc, o_s, lse_s, first, out if last else None)
+            else:
+                _merge_host(o_acc, lse_acc, o_s, lse_s, first)
+                if last:
+                    out.copy_(o_acc.to(out.dtype))
+            first = False
+        for r_ in reqs:
+            r_.wait()
+        if kv_next is not None:
+            kv_cur = kv_next
+    assert not first, "no valid keys"
+    return ulysses_gather_tokens(out, U, group=ug) if U > 1 else out
 
 
 class SeqAllToAll4D(torch.autograd.Function):
