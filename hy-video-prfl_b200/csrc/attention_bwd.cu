@@ -96,7 +96,12 @@ __device__ __forceinline__ void bulk_load_1d(void* smem_dst, const void* gsrc, u
 }
 
 // DKDV = true : resident = (K, V) of 128 keys, streamed = (Q, dO);  DKDV = false: resident = (Q, dO), streamed = (K, V).
-template <bool DKDV, bool TS>
+// QUAD (dQ kernel only): all 16 softmax-gradient warps work on EVERY unit, four threads per row with 16 columns each, instead
+// of two 8-warp groups that alternate units with two threads per row.  The stage between "S / dP computed" and "dS written"
+// is latency-bound (tcgen05.ld -> exp2 -> pack -> tcgen05.st -> arrive ~ 860 cycles with 32 columns per thread), longer
+// than the 768 tensor cycles of a unit, so with alternating groups the tensor pipe idles ~10-20 % (measured 81 %); with
+// 16 columns per thread the stage is shorter than X(u+1) (512 cycles) and dS(u) is always ready when the pipe wants it.
+template <bool DKDV, bool TS, bool QUAD = false>
 __global__ void __launch_bounds__(BWD_THREADS, 1)
 attn_bwd_kernel(const __grid_constant__ CUtensorMap tmR0, const __grid_constant__ CUtensorMap tmR1,
                 const __grid_constant__ CUtensorMap tmS0, const __grid_constant__ CUtensorMap tmS1, const AttnBwdParams p) {
@@ -104,7 +109,8 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmR0, const __grid_constant_
   constexpr int STAGES = BwdSmem<TS>::STAGES;
   constexpr int SUBW = (DKDV && TS) ? 32 : 64;  // unit width = TMEM columns of one X / Y buffer
   constexpr int UPS = SUB / SUBW;               // units per TMA stage
-  constexpr int CW = SUBW / 2;                  // columns per softmax-gradient thread (two threads per row)
+  static_assert(!QUAD || !DKDV, "QUAD is the dQ kernel's variant");
+  constexpr int CW = QUAD ? SUBW / 4 : SUBW / 2;   // columns per softmax-gradient thread (two or four threads per row)
   constexpr int XB = 0, YB = 2 * SUBW, ACC = 256, RES = DKDV ? 128 : 384;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -144,7 +150,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmR0, const __grid_constant_
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(&xfull[b], 1);
-      mbar_init(&pfull[b], 8);
+      mbar_init(&pfull[b], QUAD ? 16 : 8);
     }
     mbar_init(ofull, 1);
     fence_barrier_init();
@@ -304,14 +310,15 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmR0, const __grid_constant_
       nd_row = make_float2(d, d);
     }
     const float2 c2 = make_float2(p.scale_log2, p.scale_log2);
-    const int c0 = half * CW;                            // this thread's first fp32 column inside the unit
-    for (int u = wg; u < n_unit; u += 2) {
+    const int c0 = (QUAD ? wg * 2 + half : half) * CW;   // this thread's first fp32 column inside the unit
+    for (int u = QUAD ? 0 : wg; u < n_unit; u += QUAD ? 1 : 2) {
       const int st = (u / UPS) % STAGES, h = u % UPS;
+      const int xb = QUAD ? (u & 1) : wg;                // X / Y buffer of this unit
       const float* ld = sLD + st * 2 * SUB + h * SUBW + c0;      // -lse2 of this thread's columns; -delta is SUB floats further
       if (DKDV) mbar_wait(&sfull_ld[st], ((u / UPS) / STAGES) & 1);   // makes the bulk-copied -lse2 / -delta visible
-      mbar_wait(&xfull[wg], (u >> 1) & 1);
+      mbar_wait(&xfull[xb], (u >> 1) & 1);
       tc_fence_after();
-      const uint32_t x_addr = tmem_base + XB + wg * SUBW + c0 + lane_off, y_addr = tmem_base + YB + wg * SUBW + c0 + lane_off;
+      const uint32_t x_addr = tmem_base + XB + xb * SUBW + c0 + lane_off, y_addr = tmem_base + YB + xb * SUBW + c0 + lane_off;
 #pragma unroll
       for (int c = 0; c < CW / 16; ++c) {
         uint32_t xs[16], ys[16];
@@ -347,7 +354,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmR0, const __grid_constant_
       tmem_wait_st();
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&pfull[wg]);
+      if (lane == 0) mbar_arrive(&pfull[xb]);
     }
     // ---- epilogue: 16 warps share the accumulator read-out ----
     mbar_wait(ofull, 0);
@@ -442,6 +449,7 @@ extern "C" int prfl_attn_bwd(const void* q, int64_t q_ld_tok, int64_t q_ld_head,
     cudaError_t e = cudaFuncSetAttribute(attn_bwd_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, BwdSmem<true>::BYTES);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(attn_bwd_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, BwdSmem<false>::BYTES);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(attn_bwd_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, BwdSmem<true>::BYTES);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(attn_bwd_kernel<false, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, BwdSmem<true>::BYTES);
     if (e != cudaSuccess) return cuda_fail(e, "attn_bwd: cudaFuncSetAttribute");
     device_mark_init(&attr_mask);
   }
@@ -459,7 +467,10 @@ extern "C" int prfl_attn_bwd(const void* q, int64_t q_ld_tok, int64_t q_ld_head,
   p.out1 = nullptr; p.o1_ld_tok = p.o1_ld_head = 0;
   p.res0 = (const __nv_bfloat16*)q; p.r0_ld_tok = q_ld_tok; p.r0_ld_head = q_ld_head;
   p.res1 = (const __nv_bfloat16*)dout; p.r1_ld_tok = do_ld_tok; p.r1_ld_head = do_ld_head;
-  attn_bwd_kernel<false, true><<<dim3((Lq + BIG - 1) / BIG, H), BWD_THREADS, BwdSmem<true>::BYTES, st>>>(tQb, tDOb, tKs, tVs, p);
+  // PRFL_ATTN_BWD_DQ=pair selects the round-1 form (two alternating 8-warp groups, two threads per row) for A/B runs
+  static const bool dq_quad = [] { const char* e = getenv("PRFL_ATTN_BWD_DQ"); return !(e && e[0] == 'p'); }();
+  if (dq_quad) attn_bwd_kernel<false, true, true><<<dim3((Lq + BIG - 1) / BIG, H), BWD_THREADS, BwdSmem<true>::BYTES, st>>>(tQb, tDOb, tKs, tVs, p);
+  else attn_bwd_kernel<false, true><<<dim3((Lq + BIG - 1) / BIG, H), BWD_THREADS, BwdSmem<true>::BYTES, st>>>(tQb, tDOb, tKs, tVs, p);
   count_launch();
   PRFL_LAUNCH_CHECK("attn_bwd_dq");
   return PRFL_OK;

@@ -19,6 +19,7 @@
 #include <math.h>
 
 #include <stdlib.h>
+#include <string.h>
 
 #include <atomic>
 
@@ -33,7 +34,7 @@ constexpr int KT = 128;       // keys per KV tile
 constexpr int HD = 128;
 constexpr int TILE_BYTES = 128 * 128 * 2;  // 32 KB: any 128 x 128 bf16 tile (two 64-wide TMA boxes)
 constexpr int KV_STAGES = 2;
-constexpr int ATT_XCH = 2 * 2 * 2 * 128 * 4;   // [slot][Q tile][half][row] floats exchanged between the two threads of a row
+constexpr int ATT_XCH = 2 * 2 * 4 * 128 * 4;   // [slot][Q tile][column part][row] floats exchanged between the threads of a row
 constexpr int ATT_SMEM = 2 * TILE_BYTES + 2 * KV_STAGES * TILE_BYTES + ATT_XCH + 256 + 1024;
 
 struct AttnFwdParams {
@@ -52,11 +53,21 @@ struct AttnFwdParams {
   int n_split;       // pieces per unit along the key axis (blockIdx.y); 1 = write the final output directly
   float* part_o;     // [blockIdx.x][n_split][256][128] fp32, normalised partial outputs
   float* part_lse;   // [blockIdx.x][n_split][256]      log2-domain LSE of each partial
+  int bar_wide;      // QUAD softmax: 1 = one 512-thread barrier per (tile, KV tile) for the row-max exchange (A/B), 0 = one
+                     // 128-thread barrier per TMEM lane quadrant (the 4 warps that share rows sit on the same SM sub-partition)
 };
 
 // FMA_MASK: which of the 8 (i = 0, 4, ..., 28) second pairs of each 32-column chunk take the FMA-pipe exp2 (bit i/4):
 // 0xAA = 4 of 16 pairs (25 %), 0xEE = 37.5 %, 0xFF = 50 %, 0 = all on MUFU.
-template <int FMA_MASK>
+// QUAD: all 16 softmax warps work on Q tile 0, then Q tile 1, of every KV tile — four threads per row with 32 keys / 32
+// output columns each — instead of one 8-warp group per Q tile with two threads per row.  The S -> softmax -> P stage is
+// what the tensor pipe waits on (P_t(j) gates P.V of tile t and, behind it, S_t(j+1)); with 64 columns per thread it
+// lasts ~1 500 cycles against the 1 024 tensor cycles available to hide it.  Halving the columns per thread shortens the
+// serial part (tcgen05.ld latency, pack, tcgen05.st, fences) while the MUFU work per tile stays the same.
+// Measured and dropped (profiles/r02_attn_fwd_quad_and_prefetch_experiment.patch): fetching S in 16-column chunks one chunk
+// ahead of the exponentials (tcgen05.ld latency hidden behind math / exchange / P store) — 20.0 ms against 17.8 ms for this
+// form at L = 32 760 x 40 heads: the extra tcgen05.ld / wait / probe instructions cost more than the latency they hide.
+template <int FMA_MASK, bool QUAD = false>
 __global__ void __launch_bounds__(ATT_THREADS, 1)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                 const __grid_constant__ CUtensorMap tmV, const AttnFwdParams p) {
@@ -97,7 +108,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       mbar_init(&vfull[s], 1);
       mbar_init(&vempty[s], 1);
       mbar_init(&sfull[s], 1);
-      mbar_init(&pfull[s], 8);
+      mbar_init(&pfull[s], QUAD ? 16 : 8);
     }
     mbar_init(ofull, 1);
     fence_barrier_init();
@@ -149,9 +160,11 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       auto issue_pv = [&](int t, int vs, bool acc) {
         const uint32_t vlo = sdesc_lo(v_addr + vs * TILE_BYTES, 16384);
         const uint32_t d = tmem_base + 256 + t * 128, a = tmem_base + t * 128;
+        // packed bf16 P of keys [16k, 16k + 16): written by the thread that owns those keys at the start of its own fp32 columns
 #pragma unroll
         for (int k = 0; k < KT / 16; ++k)
-          umma_ts(d, a + (k >> 2) * 64 + (k & 3) * 8, sdesc_join(vlo + k * (2048 >> 4), HI), idesc_pv, (acc || k != 0) ? 1u : 0u);
+          umma_ts(d, a + (QUAD ? (k >> 1) * 32 + (k & 1) * 8 : (k >> 2) * 64 + (k & 3) * 8), sdesc_join(vlo + k * (2048 >> 4), HI),
+                  idesc_pv, (acc || k != 0) ? 1u : 0u);
       };
       mbar_wait(qfull, 0);
       mbar_wait(&kfull[0], 0);
@@ -184,6 +197,157 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         }
       }
       umma_commit(ofull);
+    }
+  } else if (QUAD) {
+    // ------------------------------- softmax + epilogue, four threads per row -------------------------------
+    const int part = warp >> 2;              // which 32 keys / 32 output columns
+    const int quad = warp & 3;               // TMEM lane quadrant
+    const int r = quad * 32 + lane;          // row inside a Q tile
+    const uint32_t lane_off = (uint32_t)(quad * 32) << 16;
+    float m_used[2] = {-INFINITY, -INFINITY};   // per Q tile: max the exponentials are relative to (identical in the 4 threads of a row)
+    float l_sum[2] = {0.f, 0.f};                // per Q tile: this thread's share of the row sum
+    const float2 sc2 = make_float2(p.scale_log2, p.scale_log2);
+    auto xslot = [&](int slot, int t, int pt) { return sX + ((slot * 2 + t) * 4 + pt) * 128 + r; };
+    auto row_sync = [&]() {
+      if (p.bar_wide) named_bar_sync(1, 512);
+      else named_bar_sync(2 + quad, 128);     // warps quad, quad + 4, quad + 8, quad + 12: the four parts of the same 32 rows
+    };
+    auto row_max4 = [&](int slot, int t, float mine) {
+      *xslot(slot, t, part) = mine;
+      row_sync();
+      return fmaxf(fmaxf(*xslot(slot, t, 0), *xslot(slot, t, 1)), fmaxf(*xslot(slot, t, 2), *xslot(slot, t, 3)));
+    };
+    for (int j = 0; j < n_kv; ++j) {
+#pragma unroll
+      for (int t = 0; t < 2; ++t) {
+        const uint32_t s_addr = tmem_base + t * 128 + part * 32 + lane_off;
+        const uint32_t o_addr = tmem_base + 256 + t * 128 + part * 32 + lane_off;
+        mbar_wait(&sfull[t], j & 1);
+        tc_fence_after();
+        const int valid = p.Lk - (kv0 + j) * KT - part * 32;   // my columns >= valid are padding (only the last tile is ragged)
+        uint32_t pk[16];
+        float tile_sum = 0.f, tile_max = -INFINITY;
+        auto exp_pass = [&](const float m_ref) {
+          const float2 neg_m2 = make_float2(-m_ref, -m_ref);
+          float2 acc0 = make_float2(0.f, 0.f), acc1 = make_float2(0.f, 0.f);
+          float mx0 = -INFINITY, mx1 = -INFINITY;
+          uint32_t rr[32];
+          tmem_ld32(s_addr, rr);
+          tmem_wait_ld();
+          if (valid < 32) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+              if (i >= valid) rr[i] = 0xff800000u;  // -inf
+          }
+#pragma unroll
+          for (int i = 0; i < 32; i += 4) {
+            mx0 = fmax3(mx0, __uint_as_float(rr[i]), __uint_as_float(rr[i + 1]));
+            mx1 = fmax3(mx1, __uint_as_float(rr[i + 2]), __uint_as_float(rr[i + 3]));
+            float2 xa = ffma2(make_float2(__uint_as_float(rr[i]), __uint_as_float(rr[i + 1])), sc2, neg_m2);
+            float2 xb = ffma2(make_float2(__uint_as_float(rr[i + 2]), __uint_as_float(rr[i + 3])), sc2, neg_m2);
+            float2 pa, pb;
+            pa = make_float2(fast_exp2(xa.x), fast_exp2(xa.y));
+            if ((FMA_MASK >> (i >> 2)) & 1) pb = exp2_fma2(xb);   // FMA pipe instead of MUFU (compile-time pattern)
+            else pb = make_float2(fast_exp2(xb.x), fast_exp2(xb.y));
+            acc0 = fadd2(acc0, pa);
+            acc1 = fadd2(acc1, pb);
+            pk[i >> 1] = pack_bf16x2(pa.x, pa.y);
+            pk[(i >> 1) + 1] = pack_bf16x2(pb.x, pb.y);
+          }
+          tile_sum = (acc0.x + acc0.y) + (acc1.x + acc1.y);
+          tile_max = fmaxf(mx0, mx1);
+        };
+        if (j == 0) {
+          // first tile: the reference max must be the true row max over all 128 keys (one extra read of S from TMEM)
+          float mx = -INFINITY;
+          {
+            uint32_t rr[32];
+            tmem_ld32(s_addr, rr);
+            tmem_wait_ld();
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+              if (i < valid) mx = fmaxf(mx, __uint_as_float(rr[i]));
+          }
+          m_used[t] = row_max4(0, t, mx) * p.scale_log2;
+          exp_pass(m_used[t]);
+        } else {
+          // optimistic: exponentiate against the stale max; exact unless the row max grew by more than 8 (log2 units)
+          exp_pass(m_used[t]);
+          const float m_new = fmaxf(m_used[t], row_max4(j & 1, t, tile_max) * p.scale_log2);
+          // same rows in the same lanes of the three partner warps => all four take the same (warp-uniform) branch
+          if (__any_sync(0xffffffffu, m_new > m_used[t] + 8.0f)) {
+            const float alpha = fast_exp2(m_used[t] - m_new);
+            l_sum[t] *= alpha;
+            m_used[t] = m_new;
+            uint32_t o[32];
+            tmem_ld32(o_addr, o);
+            tmem_wait_ld();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+            tmem_st32(o_addr, o);
+            exp_pass(m_used[t]);
+          }
+        }
+        l_sum[t] += tile_sum;
+        tmem_st16(s_addr, pk);          // packed columns [32 part, 32 part + 16) = my keys [32 part, 32 part + 32)
+        tmem_wait_st();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&pfull[t]);
+      }
+    }
+    // epilogue: row sum = the four parts' shares; O / l -> bf16 -> global (32 columns per thread); LSE by part 0
+    float l_tot[2];
+#pragma unroll
+    for (int t = 0; t < 2; ++t) {
+      *xslot(n_kv & 1, t, part) = l_sum[t];
+    }
+    row_sync();
+#pragma unroll
+    for (int t = 0; t < 2; ++t)
+      l_tot[t] = (*xslot(n_kv & 1, t, 0) + *xslot(n_kv & 1, t, 1)) + (*xslot(n_kv & 1, t, 2) + *xslot(n_kv & 1, t, 3));
+    mbar_wait(ofull, 0);
+    tc_fence_after();
+#pragma unroll
+    for (int t = 0; t < 2; ++t) {
+      const uint32_t o_addr = tmem_base + 256 + t * 128 + part * 32 + lane_off;
+      const int row = q0 + t * QT + r;
+      const float inv_l = 1.0f / l_tot[t];
+      const bool row_ok = row < p.Lq;
+      uint32_t o[32];
+      tmem_ld32(o_addr, o);
+      tmem_wait_ld();
+      if (p.n_split > 1) {
+        const int64_t prow = ((int64_t)blockIdx.x * p.n_split + blockIdx.y) * (2 * QT) + t * QT + r;
+        float* dst = p.part_o + prow * HD + part * 32;
+#pragma unroll
+        for (int i = 0; i < 32; i += 4)
+          *reinterpret_cast<float4*>(dst + i) = make_float4(__uint_as_float(o[i]) * inv_l, __uint_as_float(o[i + 1]) * inv_l,
+                                                            __uint_as_float(o[i + 2]) * inv_l, __uint_as_float(o[i + 3]) * inv_l);
+        if (part == 0) p.part_lse[prow] = m_used[t] + log2f(l_tot[t]);
+      } else {
+        __nv_bfloat16* orow;
+        if (p.n_peer > 0) {
+          const int rk = row_ok ? row / p.L_loc : 0;
+          orow = p.o_peer[rk] + (int64_t)(row - rk * p.L_loc) * p.o_ld_tok + (int64_t)(p.head_off + head) * p.o_ld_head;
+        } else {
+          orow = p.o + (int64_t)row * p.o_ld_tok + (int64_t)head * p.o_ld_head;
+        }
+        orow += part * 32;
+        if (row_ok) {
+#pragma unroll
+          for (int i = 0; i < 32; i += 8) {
+            uint4 v;
+            v.x = pack_bf16x2(__uint_as_float(o[i]) * inv_l, __uint_as_float(o[i + 1]) * inv_l);
+            v.y = pack_bf16x2(__uint_as_float(o[i + 2]) * inv_l, __uint_as_float(o[i + 3]) * inv_l);
+            v.z = pack_bf16x2(__uint_as_float(o[i + 4]) * inv_l, __uint_as_float(o[i + 5]) * inv_l);
+            v.w = pack_bf16x2(__uint_as_float(o[i + 6]) * inv_l, __uint_as_float(o[i + 7]) * inv_l);
+            *reinterpret_cast<uint4*>(orow + i) = v;
+          }
+          if (part == 0 && p.lse) p.lse[(int64_t)head * p.Lq + row] = (m_used[t] + log2f(l_tot[t])) * 0.6931471805599453f;
+        }
+      }
+      __syncwarp();
     }
   } else {
     // ------------------------------- softmax + epilogue -------------------------------
@@ -515,10 +679,31 @@ static int attn_fwd_launch(const void* q, int64_t q_ld_tok, int64_t q_ld_head, c
   rc = make_tmap_3d(&tmV, v, HD, (uint64_t)Lk, (uint64_t)H, (uint64_t)v_ld_tok * 2, (uint64_t)v_ld_head * 2, 64, KT, 1, 1);
   if (rc != PRFL_OK) return rc;
   // measured at L = 32 760 x 40 heads: 0 % -> 20.98 ms, 25 % -> 18.34 ms, 37.5 % -> 19.40 ms, 50 % -> 19.96 ms
-  auto kern = attn_fwd_kernel<0xAA>;
+  // Default: four threads per row, 12.5 % of the exponentials on the FMA pipe, one 128-thread row barrier per lane quadrant.
+  // Measured on one box, back to back, L = 32 760 x 40 heads (CUDA events, sustained): two threads per row (round 1) 19.03 ms;
+  // four threads per row with a 512-thread barrier 18.5; with per-quadrant barriers and 0 / 12.5 / 25 / 37.5 % FMA-pipe
+  // exponentials 18.3 / 17.8 / 18.3 / 17.85 ms.  PRFL_ATTN_FWD=pair | quad25 | quad37 | quad0 | quadw select the others for A/B.
+  static const int variant = [] {
+    const char* e = getenv("PRFL_ATTN_FWD");
+    if (!e) return 3;
+    if (e[0] == 'p' || e[0] == 'b') return 0;         // pair / base: the round-1 kernel
+    if (e[0] != 'q') return 3;
+    if (e[4] == '2') return 1;
+    if (e[4] == '3') return 2;
+    if (e[4] == '0') return 4;
+    return 3;
+  }();
+  static const int bar_wide = [] { const char* e = getenv("PRFL_ATTN_FWD"); return (e && e[0] == 'q' && e[strlen(e) - 1] == 'w') ? 1 : 0; }();
+  void (*kern)(CUtensorMap, CUtensorMap, CUtensorMap, AttnFwdParams) =
+      variant == 1 ? attn_fwd_kernel<0xAA, true> : variant == 2 ? attn_fwd_kernel<0xEE, true> : variant == 3 ? attn_fwd_kernel<0x88, true>
+      : variant == 4 ? attn_fwd_kernel<0x00, true> : attn_fwd_kernel<0xAA, false>;
   static unsigned long long attr_mask = 0;      // per-device bit mask; forward and autograd threads may race: the call is idempotent
   if (device_needs_init(&attr_mask)) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM);
+    cudaError_t e = cudaFuncSetAttribute(attn_fwd_kernel<0xAA, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(attn_fwd_kernel<0xAA, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(attn_fwd_kernel<0xEE, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(attn_fwd_kernel<0x88, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(attn_fwd_kernel<0x00, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM);
     if (e != cudaSuccess) return cuda_fail(e, "attn_fwd: cudaFuncSetAttribute");
     device_mark_init(&attr_mask);
   }
@@ -526,6 +711,7 @@ static int attn_fwd_launch(const void* q, int64_t q_ld_tok, int64_t q_ld_head, c
   p.o = (__nv_bfloat16*)o; p.o_ld_tok = o_ld_tok; p.o_ld_head = o_ld_head; p.lse = lse; p.Lq = Lq; p.Lk = Lk;
   p.scale_log2 = scale * 1.4426950408889634f;
   p.n_peer = n_peer; p.L_loc = L_loc; p.head_off = head_off;
+  p.bar_wide = bar_wide;
   for (int i = 0; i < 8; ++i) p.o_peer[i] = i < n_peer ? (__nv_bfloat16*)o_peers[i] : nullptr;
   SplitPlan sp = plan_split(Lq, Lk, H);
   if (ws == nullptr) {                      // no workspace from the caller: one launch over all units

@@ -12,6 +12,9 @@ Checks, on every rank:
                 2 steps with clip_grad_norm_(1.0), the dense model re-synchronised to the sharded masters in between:
                 fp32 masters agree to max-rel <= 1e-5 per tensor after each step (a layout / collective bug shows up at
                 >= 1e-2: one Adam step moves a weight by lr = 1e-3) and the two models' forward outputs stay equal
+  usp_fwd       (even world sizes) the same no-grad forward with the ranks arranged as Ulysses (world / 2) x Ring 2
+                (`parallel.initialize_usp_state`): K / V blocks travel round the ring, partial results merged by
+                `prfl_attn_merge`; vs the oracle, same tolerances
 """
 import os
 import sys
@@ -147,7 +150,23 @@ def run_checks(world: int, rank: int, verbose: bool = True) -> dict:
     res["sharded_adamw"] = {"master_max_rel": worst, "out_cos": c_o, "out_max_rel": r_o,
                             "ok": bool(worst <= ADAMW_REL and c_o >= 0.99999 and r_o <= 1e-3),
                             "what": "fp32 masters vs dense torch AdamW on all-reduced(AVG) grads, 2 steps, clip 1.0"}
-    flag = torch.tensor([1.0 if all(res[k]["ok"] for k in ("sp_fwd", "sp_bwd", "sharded_adamw")) else 0.0], device=dev)
+    # ---- Ulysses x Ring (USP): ring degree 2 over the same ranks, no-grad forward vs the oracle ------
+    keys = ["sp_fwd", "sp_bwd", "sharded_adamw"]
+    if world % 2 == 0:
+        from prfl_b200 import parallel
+        U, R = world // 2, 2
+        parallel.initialize_usp_state(U, R)
+        try:
+            with torch.no_grad():
+                out_u = m(x=[u.to(dev) for u in inp["x"]], t=inp["t"].to(dev), context=ctx, seq_len=inp["seq_len"])
+            c_u, r_u = cos_rel(out_u[0].cpu(), ref[0].detach())
+        finally:
+            parallel.initialize_sequence_parallel_state(world)          # back to plain Ulysses for the caller
+        say(f"USP (ulysses {U} x ring {R}) forward vs oracle: cos={c_u:.6f} rel={r_u:.4f}")
+        res["usp_fwd"] = {"ulysses": U, "ring": R, "cos": c_u, "max_rel": r_u, "ok": bool(c_u >= COS_MIN and r_u <= REL_MAX),
+                          "what": "no-grad forward under Ulysses x Ring (K/V blocks round the ring, LSE merge kernel) vs oracle"}
+        keys.append("usp_fwd")
+    flag = torch.tensor([1.0 if all(res[k]["ok"] for k in keys) else 0.0], device=dev)
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
     res["ok"] = bool(float(flag) == 1.0)
     return res

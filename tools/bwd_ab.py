@@ -26,7 +26,7 @@ b.record()
 torch.cuda.synchronize()
 ms = a.elapsed_time(b) / iters
 fl = 10.0 * L * L * 128 * H
-print(f"dkdv={os.environ.get('PRFL_ATTN_BWD_DKDV', 'ts')} L={L} H={H}: bwd {ms:.2f} ms = {fl / ms / 1e9:.0f} TFLOP/s algorithmic")
+print(f"dq={os.environ.get('PRFL_ATTN_BWD_DQ', 'quad')} L={L} H={H}: bwd {ms:.2f} ms = {fl / ms / 1e9:.0f} TFLOP/s algorithmic")
 from torch.profiler import ProfilerActivity, profile
 with profile(activities=[ProfilerActivity.CUDA]) as prof:
     for _ in range(3):

@@ -25,4 +25,4 @@ for _ in range(iters):
 b.record()
 torch.cuda.synchronize()
 ms = a.elapsed_time(b) / iters
-print(f"lib={os.path.basename(_lib.LIB_PATH)} L={L} H={H}: fwd {ms:.3f} ms = {4.0 * L * L * 128 * H / ms / 1e9:.0f} TFLOP/s")
+print(f"variant={os.environ.get("PRFL_ATTN_FWD", "default(quad12)")} L={L} H={H}: fwd {ms:.3f} ms = {4.0 * L * L * 128 * H / ms / 1e9:.0f} TFLOP/s")
