@@ -9,8 +9,9 @@
       optimizer-rank{r:05}-of-{w:05}.safetensors               (NOT in the reference, which saves no optimizer state,
                                                                train_prfl.py:485-491: this rank's ShardedAdamW shard)
 
-Parameter names are the reference's (the drop-in modules keep its state-dict keys).  In this build the compute weights
-are replicated, so rank 0 already holds the full state dict: there is no FULL_STATE_DICT gather.
+Parameter names are the reference's (the drop-in modules keep its state-dict keys).  In this build the bf16 compute weights
+are replicated and the fp32 masters are 1/W shards: `ShardedAdamW.full_state_dict()` gathers them for
+`save_checkpoint(..., state_dict=...)` (the FULL_STATE_DICT role).
 Cold path: plain Python + safetensors, no kernels.
 """
 from __future__ import annotations
@@ -33,12 +34,18 @@ def _config_dict(transformer) -> dict:
     return cfg
 
 
-def save_checkpoint(transformer, rank: int, output_dir: str, step: int, ema: bool = False, max_bytes: int = MAX_SHARD_BYTES) -> Optional[str]:
-    """model_utils.py:70-126.  Returns the directory written (rank <= 0) or None."""
+def save_checkpoint(transformer, rank: int, output_dir: str, step: int, ema: bool = False, max_bytes: int = MAX_SHARD_BYTES,
+                    state_dict: Optional[Dict[str, torch.Tensor]] = None) -> Optional[str]:
+    """model_utils.py:70-126.  Returns the directory written (rank <= 0) or None.
+    `state_dict`: what to write instead of `transformer.state_dict()` — with resident bf16 weights pass
+    `ShardedAdamW.full_state_dict()` (the fp32 masters gathered from the 1/W shards, a collective every rank calls), which
+    is what the reference's FSDP FULL_STATE_DICT gather yields (model_utils.py:75-86); without it the bf16 compute copies
+    are written."""
     from safetensors.torch import save_file
     if rank > 0:
         return None
-    cpu_state = {k: v.detach().to("cpu").contiguous() for k, v in transformer.state_dict().items()}
+    src = transformer.state_dict() if state_dict is None else state_dict
+    cpu_state = {k: v.detach().to("cpu").contiguous() for k, v in src.items()}
     save_dir = os.path.join(output_dir, f"checkpoint-{step}-ema" if ema else f"checkpoint-{step}")
     os.makedirs(save_dir, exist_ok=True)
     total_bytes = sum(v.numel() * v.element_size() for v in cpu_state.values())
