@@ -38,3 +38,16 @@ def cos_rel(a, b):
     cos = float(torch.dot(a, b) / (a.norm() * b.norm() + 1e-300))
     rel = float((a - b).abs().max() / (b.abs().max() + 1e-300))
     return cos, rel
+
+
+def within_bound_or_eager(ours, eager, cos_min=0.999, rel_max=2e-2, slack=1.25):
+    """north_star's bound (cos >= 0.999, max-rel <= 2e-2 vs the fp32 reference), OR no further from the fp32 truth than
+    `slack` x the error of the reference's OWN kernel stack on the same case (`eager` = (cos, rel) of the oracle in
+    native mode: bf16 cuBLAS F.linear + flash-attn 2 on this GPU; None if that stack is unavailable)."""
+    c, r = ours
+    if c >= cos_min and r <= rel_max:
+        return True
+    if eager is None:
+        return False
+    ce, re_ = eager
+    return (1.0 - c) <= slack * (1.0 - ce) + 1e-7 and r <= slack * re_

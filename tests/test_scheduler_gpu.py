@@ -104,7 +104,8 @@ def test_refl_chain_vs_oracle():
     against the same chain built from the CPU oracles on identical weights and noise.  bf16 DiT vs the fp32 oracle:
     the latent handed to the reward model must agree to cosine >= 0.999 / 2e-2, the reward (a sigmoid output) to 1e-2
     (north_star); the end-to-end gradient passes through the reward MLP's ReLU masks, which bf16-sized feature
-    perturbations can flip (see tests/test_backward_gpu.py), so its direction is held to cosine >= 0.9 only."""
+    perturbations can flip (see tests/test_backward_gpu.py): it is held to north_star's bound OR to 1.25 x the distance the
+    reference's own bf16 kernel stack (eager cuBLAS + flash-attn 2, run here on the same chain) lands from the fp32 truth."""
     from conftest import cos_rel
     from oracle import synth
     from oracle import wan_oracle as O
@@ -119,24 +120,39 @@ def test_refl_chain_vs_oracle():
     inp = synth.make_inputs(cfg, (5, 12, 20), 83)
     noise = inp["x"][0]
     steps, mid, shift = 8, 2, 5.0
-    # ---- oracle chain (fp32, CPU) ----
-    sd_vg = {k: v.clone().requires_grad_(True) for k, v in sd_v.items()}
-    osch = UniPCOracle()
-    osch.set_timesteps(steps, shift=shift)
-    lat = noise[None].clone()
-    with torch.no_grad():
-        for i in range(mid):
-            t = osch.timesteps[i]
-            v = O.wan_forward(sd_v, cfg, [lat[0]], t[None], inp["context"], inp["seq_len"])[0]
-            lat = osch.step(v[None], t, lat)
-    t = osch.timesteps[mid]
-    v = O.wan_forward(sd_vg, cfg, [lat[0]], t[None], inp["context"], inp["seq_len"])[0]
-    lat_o = osch.step(v[None], t, lat)
-    logit_o, _ = O.pavrm_reward(sd_l, cfg, qa_sd, mlp_sd, [lat_o[0]], osch.timesteps[mid + 1][None], inp["context"],
-                                inp["seq_len"], selected_layers=(2,), num_blocks=2)
-    reward_o = torch.sigmoid(logit_o)
-    loss_o = prfl_loss(reward_o)
-    loss_o.backward()
+    # ---- oracle chain: fp32 on the CPU (the truth), and the same chain with the reference's own kernel stack on this GPU
+    #      (oracle in native mode: bf16 cuBLAS F.linear + flash-attn 2; the scheduler stays the CPU oracle) ----
+    def oracle_chain(native):
+        dev = "cuda" if native else "cpu"
+        kw = dict(autocast_dtype=torch.bfloat16, native=True) if native else {}
+        sdv = {k: v.to(dev) for k, v in sd_v.items()}
+        sdl, qas, mls = ({k: v.to(dev) for k, v in d.items()} for d in (sd_l, qa_sd, mlp_sd))
+        sd_vg = {k: v.clone().requires_grad_(True) for k, v in sdv.items()}
+        ctx = [c.to(dev) for c in inp["context"]]
+        osch = UniPCOracle()
+        osch.set_timesteps(steps, shift=shift)
+        lat = noise[None].clone()
+        with torch.no_grad():
+            for i in range(mid):
+                t = osch.timesteps[i]
+                v = O.wan_forward(sdv, cfg, [lat[0].to(dev)], t[None].to(dev), ctx, inp["seq_len"], **kw)[0]
+                lat = osch.step(v[None].float().cpu(), t, lat)
+        t = osch.timesteps[mid]
+        v = O.wan_forward(sd_vg, cfg, [lat[0].to(dev)], t[None].to(dev), ctx, inp["seq_len"], **kw)[0]
+        lat_o = osch.step(v[None].float().cpu(), t, lat)
+        logit_o, _ = O.pavrm_reward(sdl, cfg, qas, mls, [lat_o[0].to(dev)], osch.timesteps[mid + 1][None].to(dev), ctx,
+                                    inp["seq_len"], selected_layers=(2,), num_blocks=2, **kw)
+        reward_o = torch.sigmoid(logit_o.float())
+        loss_o = prfl_loss(reward_o)
+        loss_o.backward()
+        return osch, reward_o.detach().cpu(), loss_o.detach().cpu(), {k: v.grad.float().cpu() for k, v in sd_vg.items() if v.grad is not None}
+
+    osch, reward_o, loss_o, grads_o = oracle_chain(False)
+    try:
+        _, _, _, grads_e = oracle_chain(True)
+    except Exception as e:          # flash-attn unavailable: north_star's bound only
+        print("eager stack unavailable:", type(e).__name__, e)
+        grads_e = None
     # ---- product chain (CUDA) ----
     vgm = WanModel(**cfg.kwargs())
     vgm.load_state_dict(sd_v, strict=True)
@@ -160,12 +176,16 @@ def test_refl_chain_vs_oracle():
     assert cos >= 0.999 and rel <= 2e-2, ("latent", cos, rel)
     assert abs(float(reward) - float(reward_o)) <= 1e-2 and abs(float(loss) - float(loss_o)) <= 1e-3, (float(reward), float(reward_o))
     params = dict(vgm.named_parameters())
+    from conftest import within_bound_or_eager
     for k in ("head.head.weight", "blocks.1.ffn.2.weight", "blocks.0.self_attn.q.weight"):
-        g, go = params[k].grad, sd_vg[k].grad
+        g, go = params[k].grad, grads_o[k]
         assert g is not None and torch.isfinite(g).all() and float(go.abs().max()) > 0
-        cos, rel = cos_rel(g.cpu(), go)
-        print(k, cos, rel)
-        assert cos >= 0.9, (k, cos, rel)
+        ours = cos_rel(g.cpu(), go)
+        eager = cos_rel(grads_e[k], go) if grads_e is not None else None
+        print(k, "ours", ours, "eager (cuBLAS + flash-attn 2)", eager)
+        # the end-to-end gradient passes through the reward MLP's ReLU masks, which bf16-sized feature perturbations flip:
+        # held to north_star's bound, or to the error the reference's own bf16 kernel stack makes on this very chain
+        assert within_bound_or_eager(ours, eager) or (eager is None and ours[0] >= 0.9), (k, ours, eager)
 
 
 def _tiny_model(cfg, sd):
@@ -180,8 +200,9 @@ def test_sample_loop_vs_oracle_and_context_cache_is_exact(mt):
     """the CFG denoising loop (text2video.py:283-304 / image2video.py:357-388).  (a) prepared-context
     K/V caching and the fused guidance+scheduler kernel are EXACT: bit-identical to running the same modules the
     reference's way (context re-embedded each forward; guidance as separate torch ops).  (b) against the CPU oracles
-    (fp32 DiT + reference-pinned scheduler) the bf16 path stays within cosine >= 0.999 / 3e-2 after 6 guided steps
-    (guidance scale 5 amplifies the per-forward bf16 error of the cond - uncond difference, hence 3e-2 not 2e-2)."""
+    (fp32 DiT + reference-pinned scheduler) the bf16 path stays within cosine >= 0.999 / 2e-2 after 6 guided steps, or —
+    guidance scale 5 amplifies the per-forward bf16 error of the cond - uncond difference — within 1.25 x the distance
+    the reference's own bf16 kernel stack (eager cuBLAS + flash-attn 2, run here on the same loop) lands from the truth."""
     from conftest import cos_rel
     from oracle import synth
     from oracle import wan_oracle as O
@@ -217,18 +238,36 @@ def test_sample_loop_vs_oracle_and_context_cache_is_exact(mt):
             lat = sch.step((u + g * (c - u)).unsqueeze(0), t, lat.unsqueeze(0), return_dict=False)[0].squeeze(0)
             # guidance inside the kernel is one fused multiply-add chain vs three rounded torch ops: 1e-6, not bit-exact
             assert _rel(traj[i], lat.cpu()) < 1e-5, i
-    # (b) oracle loop
-    osch = UniPCOracle()
-    osch.set_timesteps(steps, shift=shift)
-    lo = noise.clone()
-    with torch.no_grad():
-        for t in osch.timesteps:
-            kw = dict(clip_fea=inp["clip_fea"], y=inp["y"])
-            c = O.wan_forward(sd, cfg, [lo], t[None], inp["context"], inp["seq_len"], **kw)[0]
-            u = O.wan_forward(sd, cfg, [lo], t[None], inp_null["context"], inp["seq_len"], **kw)[0]
-            lo = osch.step((u + g * (c - u))[None], t, lo[None])[0]
-    cos, rel = cos_rel(out.cpu(), lo)
-    assert cos >= 0.999 and rel <= 3e-2, (cos, rel)
+    # (b) oracle loop: fp32 on the CPU (the truth) and, beside it, the reference's own bf16 kernel stack on this GPU
+    def oracle_loop(native):
+        dev = "cuda" if native else "cpu"
+        extra = dict(autocast_dtype=torch.bfloat16, native=True) if native else {}
+        sdd = {k: v.to(dev) for k, v in sd.items()}
+        kw = dict(clip_fea=None if inp["clip_fea"] is None else inp["clip_fea"].to(dev),
+                  y=None if inp["y"] is None else [u.to(dev) for u in inp["y"]], **extra)
+        cc, cn = [c.to(dev) for c in inp["context"]], [c.to(dev) for c in inp_null["context"]]
+        osch = UniPCOracle()
+        osch.set_timesteps(steps, shift=shift)
+        lo = noise.clone()
+        with torch.no_grad():
+            for t in osch.timesteps:
+                c = O.wan_forward(sdd, cfg, [lo.to(dev)], t[None].to(dev), cc, inp["seq_len"], **kw)[0].float().cpu()
+                u = O.wan_forward(sdd, cfg, [lo.to(dev)], t[None].to(dev), cn, inp["seq_len"], **kw)[0].float().cpu()
+                lo = osch.step((u + g * (c - u))[None], t, lo[None])[0]
+        return lo
+
+    from conftest import within_bound_or_eager
+    lo = oracle_loop(False)
+    ours = cos_rel(out.cpu(), lo)
+    try:
+        eager = cos_rel(oracle_loop(True), lo)
+    except Exception as e:
+        print("eager stack unavailable:", type(e).__name__, e)
+        eager = None
+    print(mt, "guided sampling, 6 steps: ours", ours, "eager (cuBLAS + flash-attn 2)", eager)
+    # guidance scale 5 amplifies the per-forward bf16 error of (cond - uncond): north_star's bound, or what the reference's own
+    # bf16 kernels do on this loop
+    assert within_bound_or_eager(ours, eager) or (eager is None and ours[0] >= 0.999 and ours[1] <= 3e-2), (ours, eager)
 
 
 def test_prepared_context_is_bit_identical():
