@@ -8,10 +8,13 @@ Checks, on every rank:
   sp_bwd        through the NCCL all-to-all path: the SUM over SP ranks of the partial weight / input gradients equals
                 the oracle's SP=1 gradient, same tolerances
   sharded_adamw `ShardedAdamW` (resident bf16 weights, reduce-scattered fp32 gradient shards, 1/W fp32 masters,
-                bf16 all-gather) vs dense torch.optim.AdamW on all-reduced(AVG) gradients of the replicated fp32 model,
-                2 steps with clip_grad_norm_(1.0), the dense model re-synchronised to the sharded masters in between:
-                fp32 masters agree to max-rel <= 1e-5 per tensor after each step (a layout / collective bug shows up at
-                >= 1e-2: one Adam step moves a weight by lr = 1e-3) and the two models' forward outputs stay equal
+                bf16 all-gather) vs dense torch.optim.AdamW on the replicated fp32 model, 2 steps with clip_grad_norm_(1.0):
+                (i) the gradient shards, gathered back, equal the all-reduced(AVG) dense gradients to 1e-5 of each tensor's
+                largest gradient (NCCL's reduce-scatter and all-reduce sum in different orders for W > 2); (ii) given the
+                SAME reduced gradients the fp32 masters agree to max-rel <= 2e-6 per tensor after each step (the dense
+                model is re-synchronised to the sharded masters in between) and the two models' outputs stay equal.  Feeding
+                each side its own reduction instead lets Adam amplify the order-of-summation noise of this model's
+                noise-level gradients (measured at W = 8: masters differ by 3e-5 with both sides correct)
   usp_fwd       (even world sizes) the same no-grad forward with the ranks arranged as Ulysses (world / 2) x Ring 2
                 (`parallel.initialize_usp_state`): K / V blocks travel round the ring, partial results merged by
                 `prfl_attn_merge`; vs the oracle, same tolerances
@@ -29,7 +32,7 @@ from conftest import cos_rel  # noqa: E402
 from oracle import synth  # noqa: E402
 from oracle import wan_oracle as O  # noqa: E402
 
-COS_MIN, REL_MAX, LOGIT_TOL, ADAMW_REL = 0.999, 2e-2, 1e-2, 1e-5
+COS_MIN, REL_MAX, LOGIT_TOL, ADAMW_REL, GRAD_REL = 0.999, 2e-2, 1e-2, 2e-6, 1e-5
 
 
 def run_checks(world: int, rank: int, verbose: bool = True) -> dict:
@@ -38,7 +41,7 @@ def run_checks(world: int, rank: int, verbose: bool = True) -> dict:
     from prfl_b200.pavrm import PavrmScorer
     from prfl_b200.sharding import ShardedAdamW
     dev = torch.device("cuda", torch.cuda.current_device())
-    res = {"tolerance": {"cos_min": COS_MIN, "max_rel": REL_MAX, "logit_abs": LOGIT_TOL, "adamw_max_rel": ADAMW_REL}}
+    res = {"tolerance": {"cos_min": COS_MIN, "max_rel": REL_MAX, "logit_abs": LOGIT_TOL, "adamw_max_rel": ADAMW_REL, "grad_max_rel": GRAD_REL}}
 
     def say(*a):
         if verbose:
@@ -120,18 +123,32 @@ def run_checks(world: int, rank: int, verbose: bool = True) -> dict:
     opt_a = ShardedAdamW(a, lr=1e-3, weight_decay=0.01).attach_hooks()                  # resident bf16 + sharded state (auto)
     assert opt_a.resident
     opt_b = torch.optim.AdamW(b.parameters(), lr=1e-3, weight_decay=0.01)
-    worst = 0.0
+    names_b = dict(b.named_parameters())
+    worst, worst_g = 0.0, 0.0
     for step in range(2):
         gi = torch.Generator().manual_seed(200 + step)
         xin = [torch.randn(inp["x"][0].shape, generator=gi).to(dev)]
         cot2 = torch.randn(ref[0].shape, generator=gi).to(dev)
         (a(x=xin, t=inp["t"].to(dev), context=ctx, seq_len=inp["seq_len"])[0] * cot2).sum().backward()
-        opt_a.step(max_norm=1.0)
         (b(x=xin, t=inp["t"].to(dev), context=ctx, seq_len=inp["seq_len"])[0] * cot2).sum().backward()
-        for p in b.parameters():
-            if p.grad is None:
-                p.grad = torch.zeros_like(p)                 # FSDP flat-parameter semantics (unused parameters still decay)
-            dist.all_reduce(p.grad, op=dist.ReduceOp.AVG)
+        # (i) the reduce-scattered gradient shards, gathered back, against plain all-reduced(AVG) gradients of the dense model:
+        #     checks the staging layout, the sink and the collectives (summation order differs between NCCL's reduce-scatter
+        #     and all-reduce for W > 2, hence a tolerance relative to each tensor's largest gradient)
+        shards = opt_a.reduce_gradients()
+        for ui, u in enumerate(opt_a.units):
+            full = torch.empty(u.shard * world, dtype=torch.float32, device=dev)
+            dist.all_gather_into_tensor(full, shards[ui].contiguous())
+            for n, (o, cnt, shp) in u.offsets.items():
+                p_b = names_b[(u.sink.prefix + n) if u.kind == "resident" else n]
+                if p_b.grad is None:
+                    p_b.grad = torch.zeros_like(p_b)             # FSDP flat-parameter semantics (unused parameters still decay)
+                dist.all_reduce(p_b.grad, op=dist.ReduceOp.AVG)
+                got = full[o:o + cnt].view(shp)
+                worst_g = max(worst_g, float((got - p_b.grad.float()).abs().max() / (p_b.grad.float().abs().max() + 1e-30)))
+                # (ii) hand the dense optimizer the SAME reduced gradient, so that the optimizer comparison below is not at the
+                #      mercy of Adam dividing rounding-level differences of noise-level gradients by their own magnitude
+                p_b.grad.copy_(got)
+        opt_a.step(max_norm=1.0)
         torch.nn.utils.clip_grad_norm_(b.parameters(), 1.0)
         opt_b.step()
         opt_b.zero_grad(set_to_none=True)
@@ -139,17 +156,19 @@ def run_checks(world: int, rank: int, verbose: bool = True) -> dict:
         for k, v in b.state_dict().items():
             d = float((full[k].float() - v.detach().float().cpu()).abs().max() / (v.detach().float().abs().max().cpu() + 1e-12))
             worst = max(worst, d)
-        # re-synchronise the dense model to the sharded masters (see tests/test_sharding_gpu.py: Adam amplifies the
-        # noise-dominated cross-attention gradients of this tiny model; with identical weights step 2 is as strict as step 1)
+        # re-synchronise the dense model to the sharded masters (see tests/test_sharding_gpu.py: with identical weights both
+        # sides compute the same gradients again and step 2 is as strict as step 1)
         b.load_state_dict({k: v.to(dev) for k, v in full.items()}, strict=True)
     with torch.no_grad():
         oa = a(x=xin, t=inp["t"].to(dev), context=ctx, seq_len=inp["seq_len"])[0]
         ob = b(x=xin, t=inp["t"].to(dev), context=ctx, seq_len=inp["seq_len"])[0]
     c_o, r_o = cos_rel(oa.cpu(), ob.cpu())
-    say(f"ShardedAdamW (resident bf16, W={world}) vs dense AdamW after 2 steps: master max-rel {worst:.2e}; outputs cos={c_o:.6f} rel={r_o:.2e}")
-    res["sharded_adamw"] = {"master_max_rel": worst, "out_cos": c_o, "out_max_rel": r_o,
-                            "ok": bool(worst <= ADAMW_REL and c_o >= 0.99999 and r_o <= 1e-3),
-                            "what": "fp32 masters vs dense torch AdamW on all-reduced(AVG) grads, 2 steps, clip 1.0"}
+    say(f"ShardedAdamW (resident bf16, W={world}) vs dense AdamW, 2 steps: gradient shards vs all-reduce max-rel {worst_g:.2e}; "
+        f"masters max-rel {worst:.2e}; outputs cos={c_o:.6f} rel={r_o:.2e}")
+    res["sharded_adamw"] = {"grad_max_rel": worst_g, "master_max_rel": worst, "out_cos": c_o, "out_max_rel": r_o,
+                            "ok": bool(worst_g <= GRAD_REL and worst <= ADAMW_REL and c_o >= 0.99999 and r_o <= 1e-3),
+                            "what": "reduce-scattered fp32 gradient shards vs all-reduced(AVG) dense gradients; fp32 masters vs dense torch "
+                                    "AdamW given the same reduced gradients, 2 steps, clip 1.0"}
     # ---- Ulysses x Ring (USP): ring degree 2 over the same ranks, no-grad forward vs the oracle ------
     keys = ["sp_fwd", "sp_bwd", "sharded_adamw"]
     if world % 2 == 0:

@@ -181,7 +181,7 @@ def measure(blocks: int, m_list=(2,), latent=LATENT_720P, steps: int = 2, i2v: b
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--blocks", type=int, default=0, help="VGM depth (0 = the largest that fits this world size)")
-    ap.add_argument("--m", default="2", help="comma-separated numbers of no-grad forwards (mid_timestep) to time")
+    ap.add_argument("--nograd", dest="m", default="2", help="comma-separated numbers of no-grad forwards (mid_timestep) to time")
     ap.add_argument("--latent", default="21,90,160")
     ap.add_argument("--steps", type=int, default=2)
     ap.add_argument("--t2v", action="store_true", help="text-to-video architecture (default: I2V, in_dim 36 + CLIP tokens + y)")
