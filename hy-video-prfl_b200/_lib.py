@@ -46,6 +46,7 @@ _SIGS = {
     "prfl_attn_fwd_p2p": (C.c_int, [_p, _i64, _i64, _p, _i64, _i64, _p, _i64, _i64, _p, _i32, _i32, _i32, _i64, _i64, _p, _i32, _i32,
                                     _i32, _f32, _p, _p]),
     "prfl_a2a_scatter_p2p": (C.c_int, [_p, _i64, _i64, _p, _i32, _i32, _i32, _i32, _p]),
+    "prfl_a2a_gather_p2p": (C.c_int, [_p, _i64, _i64, _p, _i64, _i64, _i32, _i32, _i32, _i32, _p]),
     "prfl_patchify": (C.c_int, [_p, _i32, _p, _i32, _p, _i32, _i32, _i32, _p]),
     "prfl_patchify_bwd": (C.c_int, [_p, _i32, _i32, _p, _i32, _i32, _i32, _p]),
     "prfl_unpatchify": (C.c_int, [_p, _p, _i32, _i32, _i32, _i32, _i32, _p]),

@@ -306,6 +306,24 @@ __global__ void a2a_scatter_p2p_kernel(const __nv_bfloat16* __restrict__ strided
   }
 }
 
+// The reverse exchange (attention layout -> token-chunk layout) as direct peer stores: this rank holds all L tokens of its
+// Hl heads; token chunk p goes to rank p, at this rank's head offset:
+//   peer[p][t * dst_ld_tok + (rank*Hl + hl) * dst_ld_head + :] = src[(p*L_loc + t) * src_ld_tok + hl * src_ld_head + :]
+__global__ void a2a_gather_p2p_kernel(const __nv_bfloat16* __restrict__ src, int64_t src_ld_tok, int64_t src_ld_head, PeerPtrs peers,
+                                      int64_t dst_ld_tok, int64_t dst_ld_head, int L_loc, int Hl, int P, int rank) {
+  const int64_t total = (int64_t)P * L_loc * Hl * 16;
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+    int piece = (int)(idx & 15);
+    int64_t t = idx >> 4;
+    int hl = (int)(t % Hl);
+    t /= Hl;                                   // global token index p * L_loc + tok
+    int p = (int)(t / L_loc);
+    int tok = (int)(t - (int64_t)p * L_loc);
+    const uint4 v = *reinterpret_cast<const uint4*>(src + t * src_ld_tok + (int64_t)hl * src_ld_head + piece * 8);
+    *reinterpret_cast<uint4*>(peers.p[p] + (int64_t)tok * dst_ld_tok + (int64_t)(rank * Hl + hl) * dst_ld_head + piece * 8) = v;
+  }
+}
+
 template <typename F>
 static int dispatch_nch(int C, F&& f) {
   switch (C / 256) {
@@ -482,6 +500,27 @@ int prfl_a2a_scatter_p2p(const void* strided, int64_t ld_tok, int64_t ld_head, v
                                                                                                ld_head, pp, L_loc, H, P, rank);
   count_launch();
   PRFL_LAUNCH_CHECK("a2a_scatter_p2p");
+  return PRFL_OK;
+}
+
+int prfl_a2a_gather_p2p(const void* src, int64_t src_ld_tok, int64_t src_ld_head, void* const* peer_dst, int64_t dst_ld_tok,
+                        int64_t dst_ld_head, int L_loc, int Hl, int P, int rank, prfl_stream_t stream) {
+  PRFL_CHECK_ARCH();
+  PRFL_REQUIRE(L_loc > 0 && Hl > 0 && P >= 1 && P <= 8 && rank >= 0 && rank < P && peer_dst, PRFL_E_SHAPE,
+               "a2a_gather_p2p: L_loc=%d Hl=%d P=%d rank=%d", L_loc, Hl, P, rank);
+  PRFL_REQUIRE(aligned16(src) && src_ld_tok % 8 == 0 && src_ld_head % 8 == 0 && dst_ld_tok % 8 == 0 && dst_ld_head % 8 == 0, PRFL_E_ALIGN,
+               "a2a_gather_p2p: alignment");
+  PeerPtrs pp;
+  for (int i = 0; i < 8; ++i) {
+    pp.p[i] = i < P ? (__nv_bfloat16*)peer_dst[i] : nullptr;
+    PRFL_REQUIRE(i >= P || aligned16(peer_dst[i]), PRFL_E_ALIGN, "a2a_gather_p2p: peer pointer %d not 16-byte aligned", i);
+  }
+  int64_t total = (int64_t)P * L_loc * Hl * 16;
+  int64_t blocks = (total + 255) / 256, cap = (int64_t)sm_count() * 16;
+  a2a_gather_p2p_kernel<<<(int)(blocks < cap ? blocks : cap), 256, 0, (cudaStream_t)stream>>>(
+      (const __nv_bfloat16*)src, src_ld_tok, src_ld_head, pp, dst_ld_tok, dst_ld_head, L_loc, Hl, P, rank);
+  count_launch();
+  PRFL_LAUNCH_CHECK("a2a_gather_p2p");
   return PRFL_OK;
 }
 

@@ -80,11 +80,17 @@ def block_forward(blk, x: torch.Tensor, em: torch.Tensor, ctx: torch.Tensor, seq
         a1 = usp_attention(q3, k3, v3, klen)
         qg = kg = vg = og = None
     else:
-        p2p = None if keep else get_p2p_ulysses(M * P, n, x.device)
-        if p2p is not None:
+        p2p = get_p2p_ulysses(M * P, n, x.device)
+        if p2p is not None and not keep:
             # no-grad forward: both exchanges are peer stores fused into our own kernels (no NCCL, no staging copies)
             a1 = p2p.attention(q3, k3, v3, klen)                                             # [M, n, d] (symmetric buffer)
             qg = kg = vg = og = None
+        elif p2p is not None:
+            # recompute-forward of a checkpointed block: the same peer stores, but q / k / v / o stay on this rank in the
+            # attention layout for the backward (views of the symmetric buffers: valid until the next block's exchange)
+            qg, kg, vg = p2p.scatter_qkv(q3, k3, v3)                                         # [L, n/P, d]
+            og, lse1 = ops.attn_fwd(qg, kg[:klen], vg[:klen], need_lse=True)
+            a1 = p2p.gather_out(og)                                                          # [M, n, d] (symmetric buffer)
         else:
             qg, kg, vg = (ulysses_scatter_tokens(t, P) for t in (q3, k3, v3))                # [L, n/P, d]
             if keep:
@@ -296,14 +302,19 @@ def block_backward(blk, st: Dict, dx: torch.Tensor, need_ctx_grad: bool, need_w:
         ops.attn_bwd(q3, k3[:klen], v3[:klen], st["a1"].unflatten(1, (n, d)), da1.unflatten(1, (n, d)), st["lse1"],
                      dq=dq3, dk=dk3[:klen], dv=dv3[:klen])
     else:
-        dog = ulysses_scatter_tokens(da1.unflatten(1, (n, d)), P)                             # [L, n/P, d]
+        p2p = get_p2p_ulysses(M * P, n, dx.device)
+        da1_3 = da1.unflatten(1, (n, d))
+        dog = p2p.scatter_grad(da1_3) if p2p is not None else ulysses_scatter_tokens(da1_3, P)   # [L, n/P, d]
         L = dog.shape[0]
         dkg = (torch.zeros if klen < L else torch.empty)(L, n // P, d, dtype=torch.bfloat16, device=dx.device)
         dvg = torch.zeros_like(dkg) if klen < L else torch.empty_like(dkg)
         dqg, _, _ = ops.attn_bwd(st["qg"], st["kg"][:klen], st["vg"][:klen], st["og"], dog, st["lse1"], dk=dkg[:klen], dv=dvg[:klen])
-        dqkv = torch.empty(M, 3 * C, dtype=torch.bfloat16, device=dx.device)
-        for j, t in enumerate((dqg, dkg, dvg)):                                               # unpacked straight into the fused buffer
-            ulysses_gather_tokens(t, P, out=dqkv[:, j * C:(j + 1) * C].unflatten(1, (n, d)))
+        if p2p is not None:
+            dqkv = p2p.gather_grads(dqg, dkg, dvg)                                            # [M, 3C] symmetric buffer, written by the peers
+        else:
+            dqkv = torch.empty(M, 3 * C, dtype=torch.bfloat16, device=dx.device)
+            for j, t in enumerate((dqg, dkg, dvg)):                                           # unpacked straight into the fused buffer
+                ulysses_gather_tokens(t, P, out=dqkv[:, j * C:(j + 1) * C].unflatten(1, (n, d)))
     del da1
     qk_raw = st["qk_raw"]
     g["self_attn.norm_q.weight"] = ops.rmsnorm_rope_bwd_(qk_raw[:, :C], _f(sa.norm_q.weight), st["cos"], st["sin"], dqkv[:, :C],

@@ -300,6 +300,16 @@ def a2a_scatter_p2p(strided: torch.Tensor, peer_recv_ptrs, P: int, rank: int):
                                      rank, _stream()), "prfl_a2a_scatter_p2p")
 
 
+def a2a_gather_p2p(src: torch.Tensor, peer_dst_ptrs, dst_ld_tok: int, dst_ld_head: int, P: int, rank: int):
+    """The reverse exchange as direct NVLink stores: src [P*L_loc, Hl, 128] (this rank's heads, all tokens);
+    peer[p][t*dst_ld_tok + (rank*Hl + hl)*dst_ld_head + :] = src[p*L_loc + t, hl, :]."""
+    _req(src, bf16, "a2a_gather_p2p.src")
+    L, Hl, d = src.shape
+    assert d == 128 and src.stride(2) == 1 and L % P == 0 and len(peer_dst_ptrs) == P
+    check(lib().prfl_a2a_gather_p2p(_p(src), src.stride(0), src.stride(1), _ptr_array(peer_dst_ptrs), int(dst_ld_tok), int(dst_ld_head),
+                                    L // P, Hl, P, rank, _stream()), "prfl_a2a_gather_p2p")
+
+
 def attn_fwd_p2p(q, k, v, o_peer_ptrs, L_loc: int, head_off: int, H_total: int, scale: Optional[float] = None):
     """attn_fwd whose epilogue stores row i into rank (i // L_loc)'s [L_loc, H_total, 128] buffer (peer pointers)."""
     for t, n in ((q, "q"), (k, "k"), (v, "v")):
@@ -490,7 +500,7 @@ NVTX_FAMILIES = {
     "norm": ("ln_mod", "ln_mod_split", "rmsnorm_rope_", "ln_mod_bwd", "rmsnorm_rope_bwd_", "colsum", "gate_bwd", "cast_bf16"),
     "gemm": ("gemm",),
     "attention": ("attn_fwd", "attn_bwd", "attn_fwd_p2p", "attn_merge_"),
-    "exchange": ("a2a_pack", "a2a_scatter_p2p"),
+    "exchange": ("a2a_pack", "a2a_scatter_p2p", "a2a_gather_p2p"),
     "patch": ("patchify", "patchify_bwd", "unpatchify", "unpatchify_bwd"),
     "reward": ("sq_pool", "sq_pool_bwd"),
     "scheduler": ("unipc_step", "scale2"),

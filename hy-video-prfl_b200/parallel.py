@@ -311,13 +311,14 @@ class P2PUlysses:
         self.P, self.rank = nccl_info.sp_size, nccl_info.rank_within_group
         self.L, self.H = L, H
         self.L_loc, self.Hl = L // self.P, H // self.P
-        self.qkv = symm_mem.empty(3, L, self.Hl, 128, dtype=torch.bfloat16, device=device)
+        self.qkv = symm_mem.empty(4, L, self.Hl, 128, dtype=torch.bfloat16, device=device)      # slab 3: dO in the backward
         self.o = symm_mem.empty(self.L_loc, H, 128, dtype=torch.bfloat16, device=device)
         self.h_qkv = symm_mem.rendezvous(self.qkv, nccl_info.group)
         self.h_o = symm_mem.rendezvous(self.o, nccl_info.group)
         self.qkv_ptrs = [int(p) for p in self.h_qkv.buffer_ptrs]
         self.o_ptrs = [int(p) for p in self.h_o.buffer_ptrs]
         self.slab = L * self.Hl * 128 * 2
+        self.dqkv = self.h_dqkv = self.dqkv_ptrs = None        # [L_loc, 3*H*128] fused gradient buffer, created on first training use
 
     def attention(self, q3: torch.Tensor, k3: torch.Tensor, v3: torch.Tensor, klen: int) -> torch.Tensor:
         """q3/k3/v3: local [L/P, H, 128] bf16 views.  Returns this rank's [L/P, H, 128] attention output (a view of the
@@ -329,6 +330,47 @@ class P2PUlysses:
         ops.attn_fwd_p2p(self.qkv[0], self.qkv[1][:klen], self.qkv[2][:klen], self.o_ptrs, self.L_loc, self.rank * self.Hl, self.H)
         self.h_o.barrier(channel=1)
         return self.o
+
+
+    # ---- training path (recompute-forward + backward of a checkpointed block): same peer stores, nothing fused into the
+    #      attention kernels because the backward needs q / k / v / o in the attention layout on this rank ----------------
+    def scatter_qkv(self, q3: torch.Tensor, k3: torch.Tensor, v3: torch.Tensor):
+        """local [L/P, H, 128] views -> this rank's [L, H/P, 128] q, k, v (views of the symmetric buffer, valid until the next
+        scatter; the backward of the same block runs before that)."""
+        from . import ops
+        for j, t in enumerate((q3, k3, v3)):
+            ops.a2a_scatter_p2p(t, [p + j * self.slab for p in self.qkv_ptrs], self.P, self.rank)
+        self.h_qkv.barrier(channel=0)
+        return self.qkv[0], self.qkv[1], self.qkv[2]
+
+    def gather_out(self, og: torch.Tensor) -> torch.Tensor:
+        """attention output [L, H/P, 128] of this rank's heads -> this rank's tokens [L/P, H, 128] (the symmetric buffer)."""
+        from . import ops
+        ops.a2a_gather_p2p(og, self.o_ptrs, self.H * 128, 128, self.P, self.rank)
+        self.h_o.barrier(channel=1)
+        return self.o
+
+    def scatter_grad(self, do3: torch.Tensor) -> torch.Tensor:
+        """dL/d(attention output) of this rank's tokens [L/P, H, 128] -> [L, H/P, 128] (slab 3 of the symmetric buffer)."""
+        from . import ops
+        ops.a2a_scatter_p2p(do3, [p + 3 * self.slab for p in self.qkv_ptrs], self.P, self.rank)
+        self.h_qkv.barrier(channel=0)
+        return self.qkv[3]
+
+    def gather_grads(self, dqg: torch.Tensor, dkg: torch.Tensor, dvg: torch.Tensor) -> torch.Tensor:
+        """dq, dk, dv [L, H/P, 128] of this rank's heads -> the fused [L/P, 3*H*128] gradient of this rank's tokens, written by
+        the peers straight into the column blocks of a symmetric buffer (no unpack, no concatenation)."""
+        import torch.distributed._symmetric_memory as symm_mem
+        from . import ops
+        C = self.H * 128
+        if self.dqkv is None:
+            self.dqkv = symm_mem.empty(self.L_loc, 3 * C, dtype=torch.bfloat16, device=dqg.device)
+            self.h_dqkv = symm_mem.rendezvous(self.dqkv, nccl_info.group)
+            self.dqkv_ptrs = [int(p) for p in self.h_dqkv.buffer_ptrs]
+        for j, t in enumerate((dqg, dkg, dvg)):
+            ops.a2a_gather_p2p(t, [p + j * C * 2 for p in self.dqkv_ptrs], 3 * C, 128, self.P, self.rank)
+        self.h_dqkv.barrier(channel=0)
+        return self.dqkv
 
 
 _p2p_cache = {}

@@ -220,6 +220,14 @@ int prfl_a2a_pack(void* strided, int64_t ld_tok, int64_t ld_head, void* packed, 
  * where peer_recv is a HOST array of P peer-mapped device pointers to each rank's [P*L_loc, H/P, 128] receive buffer. */
 int prfl_a2a_scatter_p2p(const void* strided, int64_t ld_tok, int64_t ld_head, void* const* peer_recv, int L_loc, int H, int P,
                          int rank, prfl_stream_t stream);
+/* The reverse exchange (the attention-output all-to-all of model.py:196 and, in backward, the dq / dk / dv exchanges that
+ * autograd derives from model.py:183-186) as direct peer stores: this rank holds all P*L_loc tokens of its Hl = H/P heads
+ * (src, element (t, hl, d) at t*src_ld_tok + hl*src_ld_head + d); token chunk p goes to rank p at this rank's head offset:
+ *   peer_dst[p][t*dst_ld_tok + (rank*Hl + hl)*dst_ld_head + d] = src[(p*L_loc + t), hl, d]
+ * peer_dst: HOST array of P peer-mapped device pointers (e.g. each rank's [L_loc, H, 128] buffer, or a column block of its
+ * fused [L_loc, 3*H*128] dQKV buffer: dst_ld_tok = 3*H*128). */
+int prfl_a2a_gather_p2p(const void* src, int64_t src_ld_tok, int64_t src_ld_head, void* const* peer_dst, int64_t dst_ld_tok,
+                        int64_t dst_ld_head, int L_loc, int Hl, int P, int rank, prfl_stream_t stream);
 
 /* ---- PRFL chain glue: scheduler step ------------------------------------------------------------
  * One FlowUniPCMultistepScheduler.step (diffusers_lite/wan/utils/fm_solvers_unipc.py:655-739: convert_model_output

@@ -169,6 +169,26 @@ def test_attn_fwd_key_split_tail(ops, Lq, Lk, H):
     assert torch.isfinite(dq.float()).all() and torch.isfinite(dk.float()).all() and torch.isfinite(dv.float()).all()
 
 
+@pytest.mark.parametrize("Lq,blocks,H", [(300, (200, 137, 64), 2), (1000, (512, 512), 3), (96, (96,), 2)])
+def test_attn_merge_ring_blocks(ops, Lq, blocks, H):
+    """prfl_attn_merge (ring attention, xdit_context_parallel.py:214-219 / xfuser): attention over key blocks folded in one at
+    a time == attention over the concatenated keys; the last fold also emits bf16."""
+    q = _rand(Lq, H, 128, dtype=torch.bfloat16, seed=50)
+    ks = [_rand(n, H, 128, dtype=torch.bfloat16, seed=51 + i) for i, n in enumerate(blocks)]
+    vs = [_rand(n, H, 128, dtype=torch.bfloat16, seed=61 + i) for i, n in enumerate(blocks)]
+    acc = torch.empty(Lq, H, 128, dtype=torch.float32, device="cuda")
+    lse = torch.empty(H, Lq, dtype=torch.float32, device="cuda")
+    out = torch.empty(Lq, H, 128, dtype=torch.bfloat16, device="cuda")
+    for i, (k, v) in enumerate(zip(ks, vs)):
+        o_i, lse_i = ops.attn_fwd(q, k, v, need_lse=True)
+        ops.attn_merge_(acc, lse, o_i, lse_i, i == 0, out if i == len(blocks) - 1 else None)
+    ref, lse_ref = _attn_ref(q, torch.cat(ks), torch.cat(vs), 1 / math.sqrt(128))
+    cos, rel = cos_rel(out, ref)
+    assert cos > 0.9999 and rel < 2e-2, (cos, rel)
+    assert torch.equal(out, acc.bfloat16())
+    assert float((lse - lse_ref).abs().max()) < 2e-3
+
+
 def test_attn_fwd_strided_and_peaked(ops):
     """q/k/v as slices of one fused [L, 3, H, 128] buffer; large-magnitude scores exercise the lazy rescale."""
     L, H = 700, 2
