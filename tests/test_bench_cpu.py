@@ -1,0 +1,45 @@
+"""CPU: the parts of bench.py that need no GPU — the reference arm (`--impl reference`: the oracle port on the host cores)
+prints one JSON line that carries the contract's keys and the SAME `config` dict as the GPU arm; `roofline.traffic` is read
+from the committed ncu summary; the PRFL-step depth rule."""
+import json
+import os
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_reference_arm_line_and_config_match():
+    env = dict(os.environ, OMP_NUM_THREADS="8")
+    res = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0"],
+                         capture_output=True, text=True, timeout=900, env=env, cwd=ROOT)
+    assert res.returncode == 0, res.stderr[-2000:]
+    line = json.loads([l for l in res.stdout.splitlines() if l.startswith("{")][-1])
+    for k in ("impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "dtype", "data",
+              "config", "cpu_baseline", "e2e"):
+        assert k in line, k
+    assert line["impl"] == "reference" and line["metric"] == "dit_tokens_per_s" and line["value"] > 0
+    assert line["e2e"] == {"value": line["value"], "unit": "tokens/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
+    sys.path.insert(0, ROOT)
+    import bench
+    assert line["config"] == bench.bench_config(1)                      # the GPU arm prints bench_config(world) too
+
+
+def test_traffic_comes_from_the_committed_ncu_summary():
+    sys.path.insert(0, ROOT)
+    import bench
+    traffic, src = bench.traffic_from_profiles()
+    assert src is not None and src.startswith("profiles/") and os.path.exists(os.path.join(ROOT, src))
+    algorithmic = 4.0 * 32760 * 40 * 128 * 2                              # Q, K, V, O once each
+    assert algorithmic <= traffic <= 1.5 * algorithmic
+
+
+def test_prfl_step_depth_rule():
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import prfl_step
+    L = 21 * 45 * 80
+    d = [prfl_step.fit_blocks(w, L) for w in (1, 2, 4, 8)]
+    assert d[2] == d[3] == 40 and 1 <= d[0] < d[1] < 40
+    f8, b8 = prfl_step.algorithmic_flops(L, True, 8)
+    assert abs(f8 * 8 / 163.08e12 - 1) < 0.02                            # 163.08 TFLOP per 720P block forward (+CLIP tokens)
