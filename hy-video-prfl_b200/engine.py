@@ -24,6 +24,15 @@ from .rope import rope_tables
 
 T5_CONTEXT_TOKEN_NUMBER = 512
 
+# Activation checkpointing granularity of the training path.  The reference recomputes the WHOLE block in backward
+# (fsdp_utils.py:23-50).  On a 180 GB B200 the self-attention output (bf16, [L, H/P, 128] in the attention layout) and its LSE
+# are cheap to keep — 98 MB per block at 720P on 8 GPUs, 3.9 GB for 40 blocks — and they let the recompute skip the one
+# kernel that is 2/3 of a block forward: "selective" (default) saves them in the forward that records the graph and reuses
+# them in backward (bit-identical gradients: the recompute would produce the same bytes); PRFL_CKPT=full restores the
+# reference's full recompute.
+import os as _os
+SAVE_ATTENTION = _os.environ.get("PRFL_CKPT", "selective").lower() != "full"
+
 
 def _f(p):
     return p.detach().float()
@@ -33,10 +42,13 @@ def _f(p):
 # forward
 # ------------------------------------------------------------------------------------------------
 def block_forward(blk, x: torch.Tensor, em: torch.Tensor, ctx: torch.Tensor, seq_len_i: int, grid: Tuple[int, int, int],
-                  first_block: bool, stash: Optional[Dict] = None, sample: int = 0) -> torch.Tensor:
+                  first_block: bool, stash: Optional[Dict] = None, sample: int = 0, save_attn: Optional[list] = None,
+                  reuse_attn: Optional[Tuple[torch.Tensor, torch.Tensor]] = None) -> torch.Tensor:
     """One sample through one block.  x: [M, C] fp32 (updated in place), em: [6, C] fp32 (modulation + e),
     ctx: [Lc, C] bf16.  With `stash` (a dict) every intermediate the backward needs is kept; x is then READ ONLY: the two
-    intermediate residual states are written to fresh buffers by the residual-epilogue GEMMs (`resid=`), no clones."""
+    intermediate residual states are written to fresh buffers by the residual-epilogue GEMMs (`resid=`), no clones.
+    `save_attn` (a list, graph-recording forward): receives (self-attention output in the attention layout, LSE) so that the
+    backward's recompute can skip the attention kernel; `reuse_attn` (recompute): that pair."""
     sa, ca = blk.self_attn, blk.cross_attn
     M, C = x.shape
     n, d = sa.num_heads, sa.head_dim
@@ -66,11 +78,16 @@ def block_forward(blk, x: torch.Tensor, em: torch.Tensor, ctx: torch.Tensor, seq
     q3, k3, v3 = (qkv[:, j * C:(j + 1) * C].unflatten(1, (n, d)) for j in range(3))
     klen = seq_len_i
     lse1 = None
+    want_lse = keep or save_attn is not None
     if not sp:
-        if keep:
+        if reuse_attn is not None:
+            a1, lse1 = reuse_attn
+        elif want_lse:
             a1, lse1 = ops.attn_fwd(q3, k3[:klen], v3[:klen], need_lse=True)
         else:
             a1 = ops.attn_fwd(q3, k3[:klen], v3[:klen])
+        if save_attn is not None:
+            save_attn.append((a1, lse1))
         qg = kg = vg = og = None
     elif nccl_info.ring_degree > 1:
         # Ulysses x Ring (xdit_context_parallel.py:190-233): inference only in the reference, no-grad only here
@@ -81,23 +98,30 @@ def block_forward(blk, x: torch.Tensor, em: torch.Tensor, ctx: torch.Tensor, seq
         qg = kg = vg = og = None
     else:
         p2p = get_p2p_ulysses(M * P, n, x.device)
-        if p2p is not None and not keep:
+        if p2p is not None and not want_lse:
             # no-grad forward: both exchanges are peer stores fused into our own kernels (no NCCL, no staging copies)
             a1 = p2p.attention(q3, k3, v3, klen)                                             # [M, n, d] (symmetric buffer)
             qg = kg = vg = og = None
         elif p2p is not None:
-            # recompute-forward of a checkpointed block: the same peer stores, but q / k / v / o stay on this rank in the
-            # attention layout for the backward (views of the symmetric buffers: valid until the next block's exchange)
+            # graph-recording forward / recompute of a checkpointed block: the same peer stores, but q / k / v / o stay on this
+            # rank in the attention layout for the backward (views of the symmetric buffers: valid until the next exchange)
             qg, kg, vg = p2p.scatter_qkv(q3, k3, v3)                                         # [L, n/P, d]
-            og, lse1 = ops.attn_fwd(qg, kg[:klen], vg[:klen], need_lse=True)
+            if reuse_attn is not None:
+                og, lse1 = reuse_attn
+            else:
+                og, lse1 = ops.attn_fwd(qg, kg[:klen], vg[:klen], need_lse=True)
             a1 = p2p.gather_out(og)                                                          # [M, n, d] (symmetric buffer)
         else:
             qg, kg, vg = (ulysses_scatter_tokens(t, P) for t in (q3, k3, v3))                # [L, n/P, d]
-            if keep:
+            if reuse_attn is not None:
+                og, lse1 = reuse_attn
+            elif want_lse:
                 og, lse1 = ops.attn_fwd(qg, kg[:klen], vg[:klen], need_lse=True)
             else:
                 og = ops.attn_fwd(qg, kg[:klen], vg[:klen])
             a1 = ulysses_gather_tokens(og, P)                                                # [M, n, d]
+        if save_attn is not None:
+            save_attn.append((og, lse1))
     a1 = a1.reshape(M, C)
     wo, bo = sa.o.operands()
     y1 = torch.empty(M, C, dtype=torch.bfloat16, device=x.device) if keep else None
@@ -350,18 +374,22 @@ class BlockFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, e, context, blk, seq_lens, grids, first_block, names, *params):
         ctx.blk, ctx.seq_lens, ctx.grids, ctx.first, ctx.names = blk, seq_lens, grids, first_block, names
-        ctx.save_for_backward(x, e, context)
         out = x.detach().clone()
         em = (_f(blk.modulation) + e.detach()).contiguous()
         cb = context.detach()
         cb = cb if cb.dtype == torch.bfloat16 else cb.to(torch.bfloat16)
+        saved = [] if (SAVE_ATTENTION and nccl_info.ring_degree == 1) else None
         for i in range(x.shape[0]):
-            block_forward(blk, out[i], em[i], cb[i].contiguous(), int(seq_lens[i]), grids[i], first_block)
+            block_forward(blk, out[i], em[i], cb[i].contiguous(), int(seq_lens[i]), grids[i], first_block, save_attn=saved)
+        ctx.n_saved = 0 if saved is None else len(saved)
+        flat = [] if saved is None else [t for pair in saved for t in pair]
+        ctx.save_for_backward(x, e, context, *flat)
         return out
 
     @staticmethod
     def backward(ctx, dout):
-        x, e, context = ctx.saved_tensors
+        x, e, context = ctx.saved_tensors[:3]
+        attn_saved = ctx.saved_tensors[3:]
         blk = ctx.blk
         B = x.shape[0]
         dx = dout.detach().float().contiguous().clone()
@@ -382,7 +410,8 @@ class BlockFn(torch.autograd.Function):
         dems, dctxs = [], []
         for i in range(B):
             st: Dict = {}
-            block_forward(blk, x[i].detach(), em[i], cb[i].contiguous(), int(ctx.seq_lens[i]), ctx.grids[i], ctx.first, st)
+            reuse = (attn_saved[2 * i], attn_saved[2 * i + 1]) if ctx.n_saved else None
+            block_forward(blk, x[i].detach(), em[i], cb[i].contiguous(), int(ctx.seq_lens[i]), ctx.grids[i], ctx.first, st, reuse_attn=reuse)
             gi, dem, dctx = block_backward(blk, st, dx[i], need_ctx, need_w, need_e, sink)
             del st
             for k, v in gi.items():

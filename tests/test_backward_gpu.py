@@ -109,3 +109,32 @@ def test_reward_chain_gradients_vs_reference():
     feats.backward(gradient=fx["grad_features"].cuda())
     cos, rel = cos_rel(x[0].grad.cpu(), fx["grad_x"][0])
     assert cos >= COS and rel <= REL, ("grad_x", cos, rel)
+
+
+def test_selective_checkpoint_gradients_bit_identical():
+    """engine.SAVE_ATTENTION (default): the graph-recording forward keeps each block's self-attention output + LSE and the
+    backward's recompute skips the attention kernel.  The saved bytes are what the recompute would produce, so every
+    gradient must be bit-identical to the reference-style full recompute (PRFL_CKPT=full)."""
+    from prfl_b200 import engine
+    fx = golden("tiny_t2v")
+    cfg = O.WanConfig(**fx["cfg"])
+    sd = synth.make_wan_state_dict(cfg, fx["seed_w"])
+    inp = synth.make_inputs(cfg, fx["latent"], fx["seed_in"])
+    g = torch.Generator().manual_seed(99)
+    grads = {}
+    prev = engine.SAVE_ATTENTION
+    try:
+        for mode in (True, False):
+            engine.SAVE_ATTENTION = mode
+            m = _model(cfg, sd)
+            x = [u.cuda().requires_grad_(True) for u in inp["x"]]
+            out = m(x=x, t=inp["t"].cuda(), context=[c.cuda() for c in inp["context"]], seq_len=inp["seq_len"])
+            if mode:
+                cot = [torch.randn(o.shape, generator=g).cuda() for o in out]
+            sum((o * c).sum() for o, c in zip(out, cot)).backward()
+            grads[mode] = {"x": x[0].grad.clone(), **{k: p.grad.clone() for k, p in m.named_parameters() if p.grad is not None}}
+    finally:
+        engine.SAVE_ATTENTION = prev
+    assert set(grads[True]) == set(grads[False])
+    for k in grads[True]:
+        assert torch.equal(grads[True][k], grads[False][k]), k

@@ -40,6 +40,6 @@ def test_prfl_step_depth_rule():
     import prfl_step
     L = 21 * 45 * 80
     d = [prfl_step.fit_blocks(w, L) for w in (1, 2, 4, 8)]
-    assert d[2] == d[3] == 40 and 1 <= d[0] < d[1] < 40
+    assert d[3] == 40 and 1 <= d[0] < d[1] < d[2] <= 40
     f8, b8 = prfl_step.algorithmic_flops(L, True, 8)
     assert abs(f8 * 8 / 163.08e12 - 1) < 0.02                            # 163.08 TFLOP per 720P block forward (+CLIP tokens)

@@ -39,7 +39,8 @@ def fit_blocks(world: int, L: int, want: int = 40, budget_gb: float = 138.0) -> 
     per_block_params = 351.4e6 + 52.4e6
     M = L / world
     fixed = 8 * per_block_params * 2 + 2 * per_block_params * 4 + 30 * M * 5120 * 2 + 8e9       # reward model, grad buffers, stash, slack
-    per_block = per_block_params * (2 + 16.0 / world) + M * 5120 * 4      # bf16 resident + (master, m, v, grad shard) fp32 / W
+    # bf16 resident + (master, m, v, grad shard) fp32 / W + saved fp32 block input + saved bf16 attention output (selective ckpt)
+    per_block = per_block_params * (2 + 16.0 / world) + M * 5120 * 4 + M * 5120 * 2
     n = int((budget_gb * 1e9 - fixed) // per_block)
     return max(1, min(want, n))
 
@@ -49,7 +50,7 @@ def measure(blocks: int, m_list=(2,), latent=LATENT_720P, steps: int = 2, i2v: b
     """Build the VGM (`blocks` 14B blocks) + frozen reward model on the current device / process group, run the step for
     every m in m_list and return a dict (rank-independent: times are max over ranks).  Frees everything on return."""
     import torch.distributed as dist
-    from prfl_b200 import _lib, sharding
+    from prfl_b200 import _lib, engine, sharding
     from prfl_b200.model import WanModel
     from prfl_b200.network import MLP, QueryAttention
     from prfl_b200.prfl import refl_chain
@@ -121,6 +122,9 @@ def measure(blocks: int, m_list=(2,), latent=LATENT_720P, steps: int = 2, i2v: b
                        f"(train_step_refl), Wan2.1-14B dims, L={L}", "blocks": blocks, "reward_blocks": 8, "sp": world, "L": L,
            "optimizer": "ShardedAdamW (fp32 master/moment shards 1/W, bf16 resident weights)" if opt and not legacy_fp32 else
                         ("ShardedAdamW (legacy fp32 replicated params)" if opt else "none (fwd+bwd only)"),
+           "checkpointing": "selective: per block the fp32 input + the bf16 self-attention output / LSE are kept, everything else is recomputed "
+                            "(FLOPs below count what is executed)" if engine.SAVE_ATTENTION else
+                            "full: only the fp32 block input is kept (the reference's per-block activation checkpointing)",
            "runs": {}}
     for _ in range(warmup):
         one_step(max(m_list))                                       # warm-up (operand caches, allocator, NCCL)
@@ -146,14 +150,17 @@ def measure(blocks: int, m_list=(2,), latent=LATENT_720P, steps: int = 2, i2v: b
         # recompute + dgrad-only (2/3 of the linear backward) of the 8 reward blocks
         lin_f = (597.7e6 * L + 4 * 5120 * 5120 * (512 + (257 if i2v else 0))) / world
         dgrad_only_blk = bwd_blk - lin_f                            # no weight-gradient GEMMs for the frozen reward blocks
-        flops = ((m + 1) * blocks + 8) * fwd_blk + blocks * (fwd_blk + bwd_blk) + 8 * (fwd_blk + dgrad_only_blk)
+        # selective checkpointing keeps the self-attention output: the recompute does not re-run that kernel, so it is not counted
+        recompute_blk = fwd_blk - (4.0 * L * L * 128 * 40 / world if engine.SAVE_ATTENTION else 0.0)
+        flops = ((m + 1) * blocks + 8) * fwd_blk + blocks * (recompute_blk + bwd_blk) + 8 * (recompute_blk + dgrad_only_blk)
         out["runs"][f"m{m}"] = {
             "s_per_step": step_ms / 1e3, "ms": avg, "loss": losses[-1],
             "dit_tokens_per_s": L * (m + 2) / (step_ms * 1e-3),    # DiT forwards per step: m no-grad + 1 grad + 1 reward
             "gpu_launches_per_step": _lib.launch_count() / steps,
             "nograd_fwd_tflops_per_gpu": m * blocks * fwd_blk / (avg["nograd_done"] * 1e-3) / 1e12 if m else None,
             "grad_fwd_tflops_per_gpu": blocks * fwd_blk / (avg["grad_fwd_done"] * 1e-3) / 1e12,
-            "bwd_tflops_per_gpu": (blocks * (fwd_blk + bwd_blk) + 8 * (fwd_blk + dgrad_only_blk)) / (avg["bwd_done"] * 1e-3) / 1e12,
+            "bwd_tflops_per_gpu": (blocks * (recompute_blk + bwd_blk) + 8 * (recompute_blk + dgrad_only_blk)) / (avg["bwd_done"] * 1e-3) / 1e12,
+            "executed_pflop_per_gpu": flops / 1e15,
             "step_tflops_per_gpu": flops / (step_ms * 1e-3) / 1e12,
             "frac_of_sustained_bf16_peak": flops / (step_ms * 1e-3) / 1e12 / pk,
         }
