@@ -314,16 +314,9 @@ def run_ours(args):
             ms = float(tt)
         return ms, t0, t1
 
-    # ---- warm-up; at N > 1 the sequence-parallel parity checks run here (they exercise NCCL, the symmetric-memory exchange,
-    #      the training all-to-all path and the sharded optimizer on this very process group) -----------------------------
-    parity = {}
-    if world > 1 and not args.no_parity:
-        sys.path.insert(0, os.path.join(ROOT, "tests"))
-        try:
-            import sp_check
-            parity.update(sp_check.run_checks(world, rank, verbose=False))
-        except Exception as e:
-            parity["sp_checks_error"] = f"{type(e).__name__}: {str(e)[:300]}"
+    # ---- the measurement proper comes FIRST; everything after it (parity legs, eager baseline, PRFL training step) is
+    #      guarded by a wall-clock watchdog that prints the line with what is finished and exits 0, so that a hang in an
+    #      optional leg (a cross-rank deadlock costs the NCCL watchdog's 10 minutes and a SIGABRT otherwise) can never lose it ----
     for _ in range(max(args.warmup, 3)):
         step_resident()
     step_e2e()
@@ -337,9 +330,77 @@ def run_ours(args):
     logit = float(logit_host)
     per_step = ms / args.steps
 
+    pk = peaks()
+    attn_ms = timer.elapsed_ms("attn_fwd_self")
+    attn_avg = sum(attn_ms) / max(1, len(attn_ms))
+    heads_local = HEADS // world
+    attn_flops = 4.0 * L * L * HD * heads_local                      # algorithmic, per launch
+    achieved = attn_flops / (attn_avg * 1e-3) / 1e12 if attn_avg > 0 else 0.0
+    traffic, traffic_src = traffic_from_profiles() if world == 1 else (None, None)
+    parity = {"reward_logit_full_workload": logit}
+    line = {
+        "metric": "dit_tokens_per_s", "value": L / (per_step * 1e-3), "unit": "tokens/s", "n_gpus": world, "steps": args.steps,
+        "warmup": max(args.warmup, 3), "ms_per_step": per_step, "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "bf16", "data": "synthetic", "config": bench_config(world),
+        "e2e": {"value": L / (ms_e2e / args.steps * 1e-3), "unit": "tokens/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4},
+        "gpu_launches": int(launches),
+        "clocks": clocks,
+        "roofline": {"kernel": "attn_fwd_kernel (self-attention fwd, tcgen05)", "bound": "tensor", "achieved": achieved,
+                     "peak": pk["tf_sust"], "unit": "TFLOP/s", "frac": achieved / pk["tf_sust"],
+                     # DRAM bytes per launch of this kernel at this shape, read from the committed `ncu --set full` summary
+                     "traffic": traffic, "traffic_source": traffic_src, "algorithmic_bytes": 4.0 * L * HEADS * HD * 2,
+                     "peak_source": pk["src"] + " sustained bf16", "launch_ms": attn_avg, "launches_timed": len(attn_ms),
+                     "share_of_step": attn_avg * len(attn_ms) / max(ms, 1e-9)},
+        "step_tflops": (8 * 41.96e12) / world / (per_step * 1e-3) / 1e12,
+        "parity": parity,
+        "prfl_step": None,
+    }
+    emit_lock = threading.Lock()
+    emitted = [False]
+    leg = ["(none)", time.time()]
+
+    def emit(note=None):
+        with emit_lock:
+            if emitted[0]:
+                return
+            emitted[0] = True
+            if note:
+                line["watchdog"] = note
+            if rank == 0:
+                try:
+                    txt = json.dumps(line)
+                except Exception as e:          # a half-built optional leg must not cost the measurement
+                    slim = {k: v for k, v in line.items() if k not in ("parity", "prfl_step", "gpu_baseline", "cpu_baseline")}
+                    slim["watchdog"] = f"{note or ''} (optional legs dropped: {type(e).__name__}: {e})"
+                    txt = json.dumps(slim)
+                print(txt, flush=True)
+
+    def watchdog():
+        while not emitted[0]:
+            time.sleep(1.0)
+            if time.time() - leg[1] > args.leg_timeout:
+                emit(f"leg '{leg[0]}' did not finish within {args.leg_timeout} s; line printed without it and the process ended")
+                time.sleep(2.0 if rank == 0 else 6.0)
+                os._exit(0)                               # a hung collective cannot be cancelled: leave without the NCCL teardown
+    threading.Thread(target=watchdog, daemon=True).start()
+
+    def begin_leg(name):
+        leg[0], leg[1] = name, time.time()
+
+    # ---- N > 1: sequence-parallel parity on this very process group (NCCL, symmetric-memory exchange, training path, sharded
+    #      optimizer, Ulysses x Ring) — the driver's GPU test box has one GPU, so this is where those numbers become visible ----
+    if world > 1 and not args.no_parity:
+        begin_leg("parity.sp_checks")
+        sys.path.insert(0, os.path.join(ROOT, "tests"))
+        try:
+            import sp_check
+            parity.update(sp_check.run_checks(world, rank, verbose=False))
+        except Exception as e:
+            parity["sp_checks_error"] = f"{type(e).__name__}: {str(e)[:300]}"
+
     # ---- same-weights parity on the bounded sample (and the CPU baseline it doubles as) ------------------------------
-    cpu_base = None
     if not args.no_cpu and not args.no_parity:
+        begin_leg("parity.same_weights_14b / cpu_baseline")
         try:
             cfg_s, inp_s = sample_inputs()
             xs = [u.to(dev) for u in inp_s["x"]]
@@ -367,18 +428,19 @@ def run_ours(args):
                     "features_cos": cos, "features_max_rel": rel, "logit_gpu": float(lg), "logit_oracle": logit_o, "dlogit": dl,
                     "tolerance": {"cos_min": 0.999, "max_rel": 2e-2, "logit_abs": 1e-2},
                     "ok": bool(cos >= 0.999 and rel <= 2e-2 and dl <= 1e-2)}
-                cpu_base = {"value": Ls / times[0], "unit": "tokens/s", "cores": cores, "kind": "port",
-                            "sample": SAMPLE_DESC + f"; 1 pass = {times[0]:.1f} s",
-                            "gpu_same_sample": {"value": Ls / (ms_s / 5 * 1e-3), "unit": "tokens/s", "ms_per_pass": ms_s / 5,
-                                                "note": "this arm on the CPU leg's exact sample and weights: the like-for-like ratio is gpu_same_sample / cpu_baseline"}}
+                if world == 1:
+                    line["cpu_baseline"] = {"value": Ls / times[0], "unit": "tokens/s", "cores": cores, "kind": "port",
+                                            "sample": SAMPLE_DESC + f"; 1 pass = {times[0]:.1f} s",
+                                            "gpu_same_sample": {"value": Ls / (ms_s / 5 * 1e-3), "unit": "tokens/s", "ms_per_pass": ms_s / 5,
+                                                                "note": "this arm on the CPU leg's exact sample and weights: the like-for-like ratio is gpu_same_sample / cpu_baseline"}}
             del xs, cs, fg
         except Exception as e:  # the GPU line must not be lost to a host-side problem
             parity["same_weights_14b"] = {"ok": False, "error": f"{type(e).__name__}: {str(e)[:300]}"}
-    barrier()
+        barrier()
 
     # ---- eager-PyTorch GPU baseline (N = 1) ---------------------------------------------------------------------------------
-    gpu_base = None
     if world == 1 and not args.no_gpu_baseline:
+        begin_leg("gpu_baseline")
         try:
             keep32 = ("time_embedding", "time_projection", "norm", "modulation", "bias")
             sd_dev = {k: (v.detach() if any(s in k for s in keep32) else v.detach().to(torch.bfloat16)) for k, v in m.state_dict().items()}
@@ -390,14 +452,15 @@ def run_ours(args):
             del sd_dev
         except Exception as e:
             gpu_base = {"unavailable": f"{type(e).__name__}: {str(e)[:200]}"}
+        line["gpu_baseline"] = gpu_base
 
     # ---- free the scoring model, then the headline: PRFL 720P training step ---------------------------------------------------
     del scorer, m, qa, mlp
     import gc
     gc.collect()
     torch.cuda.empty_cache()
-    prfl = None
     if not args.no_prfl:
+        begin_leg("prfl_step")
         sys.path.insert(0, os.path.join(ROOT, "tools"))
         try:
             import prfl_step
@@ -407,41 +470,13 @@ def run_ours(args):
             prfl["metric"] = "PRFL train s/step (BASELINE.json headline), I2V 720Px81f, 14B dims"
             if blocks < 40:
                 prfl["note"] = (f"{blocks} of 40 VGM blocks: the largest depth whose bf16 weights + 1/{world} fp32 master/AdamW shards + "
-                                "checkpointed activations fit 180 GB at this N; per-block cost is depth-independent")
+                                "checkpointed activations fit 180 GB at this N with headroom; per-block cost is depth-independent")
         except Exception as e:
             prfl = {"error": f"{type(e).__name__}: {str(e)[:400]}"}
+        line["prfl_step"] = prfl
 
-    if rank == 0:
-        pk = peaks()
-        attn_ms = timer.elapsed_ms("attn_fwd_self")
-        attn_avg = sum(attn_ms) / max(1, len(attn_ms))
-        heads_local = HEADS // world
-        attn_flops = 4.0 * L * L * HD * heads_local                      # algorithmic, per launch
-        achieved = attn_flops / (attn_avg * 1e-3) / 1e12 if attn_avg > 0 else 0.0
-        traffic, traffic_src = traffic_from_profiles() if world == 1 else (None, None)
-        parity["reward_logit_full_workload"] = logit
-        line = {
-            "metric": "dit_tokens_per_s", "value": L / (per_step * 1e-3), "unit": "tokens/s", "n_gpus": world, "steps": args.steps,
-            "warmup": max(args.warmup, 3), "ms_per_step": per_step, "higher_is_better": True, "scaling": "strong",
-            "vs_baseline": None, "dtype": "bf16", "data": "synthetic", "config": bench_config(world),
-            "e2e": {"value": L / (ms_e2e / args.steps * 1e-3), "unit": "tokens/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4},
-            "gpu_launches": int(launches),
-            "clocks": clocks,
-            "roofline": {"kernel": "attn_fwd_kernel (self-attention fwd, tcgen05)", "bound": "tensor", "achieved": achieved,
-                         "peak": pk["tf_sust"], "unit": "TFLOP/s", "frac": achieved / pk["tf_sust"],
-                         # DRAM bytes per launch of this kernel at this shape, read from the committed `ncu --set full` summary
-                         "traffic": traffic, "traffic_source": traffic_src, "algorithmic_bytes": 4.0 * L * HEADS * HD * 2,
-                         "peak_source": pk["src"] + " sustained bf16", "launch_ms": attn_avg, "launches_timed": len(attn_ms),
-                         "share_of_step": attn_avg * len(attn_ms) / max(ms, 1e-9)},
-            "step_tflops": (8 * 41.96e12) / world / (per_step * 1e-3) / 1e12,
-            "parity": parity,
-            "prfl_step": prfl,
-        }
-        if cpu_base is not None:
-            line["cpu_baseline"] = cpu_base
-        if gpu_base is not None:
-            line["gpu_baseline"] = gpu_base
-        print(json.dumps(line))
+    begin_leg("teardown")
+    emit()
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -459,6 +494,8 @@ if __name__ == "__main__":
     ap.add_argument("--no-prfl", action="store_true", help="skip the PRFL 720P training-step leg")
     ap.add_argument("--prfl-blocks", type=int, default=0, help="VGM depth of the training-step leg (0 = the largest that fits)")
     ap.add_argument("--prfl-steps", type=int, default=2)
+    ap.add_argument("--leg-timeout", type=int, default=300, help="seconds any post-measurement leg may take before the line is "
+                    "printed without it and the process exits (0 hangs are expected; this bounds the cost of one)")
     a = ap.parse_args()
     if a.impl == "reference":
         run_reference(a)

@@ -318,7 +318,11 @@ class P2PUlysses:
         self.qkv_ptrs = [int(p) for p in self.h_qkv.buffer_ptrs]
         self.o_ptrs = [int(p) for p in self.h_o.buffer_ptrs]
         self.slab = L * self.Hl * 128 * 2
-        self.dqkv = self.h_dqkv = self.dqkv_ptrs = None        # [L_loc, 3*H*128] fused gradient buffer, created on first training use
+        # [L_loc, 3*H*128] fused gradient buffer of the training path.  Created here, with the other buffers, while every rank
+        # is at the same quiescent point (the rendezvous is a host-side collective): not lazily in the middle of a backward.
+        self.dqkv = symm_mem.empty(self.L_loc, 3 * H * 128, dtype=torch.bfloat16, device=device)
+        self.h_dqkv = symm_mem.rendezvous(self.dqkv, nccl_info.group)
+        self.dqkv_ptrs = [int(p) for p in self.h_dqkv.buffer_ptrs]
 
     def attention(self, q3: torch.Tensor, k3: torch.Tensor, v3: torch.Tensor, klen: int) -> torch.Tensor:
         """q3/k3/v3: local [L/P, H, 128] bf16 views.  Returns this rank's [L/P, H, 128] attention output (a view of the
@@ -360,13 +364,8 @@ class P2PUlysses:
     def gather_grads(self, dqg: torch.Tensor, dkg: torch.Tensor, dvg: torch.Tensor) -> torch.Tensor:
         """dq, dk, dv [L, H/P, 128] of this rank's heads -> the fused [L/P, 3*H*128] gradient of this rank's tokens, written by
         the peers straight into the column blocks of a symmetric buffer (no unpack, no concatenation)."""
-        import torch.distributed._symmetric_memory as symm_mem
         from . import ops
         C = self.H * 128
-        if self.dqkv is None:
-            self.dqkv = symm_mem.empty(self.L_loc, 3 * C, dtype=torch.bfloat16, device=dqg.device)
-            self.h_dqkv = symm_mem.rendezvous(self.dqkv, nccl_info.group)
-            self.dqkv_ptrs = [int(p) for p in self.h_dqkv.buffer_ptrs]
         for j, t in enumerate((dqg, dkg, dvg)):
             ops.a2a_gather_p2p(t, [p + j * C * 2 for p in self.dqkv_ptrs], 3 * C, 128, self.P, self.rank)
         self.h_dqkv.barrier(channel=0)

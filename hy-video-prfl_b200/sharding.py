@@ -305,6 +305,37 @@ class ShardedAdamW:
         if first.is_cuda and self.world > 1:
             self._comm = torch.cuda.Stream(device=first.device)
 
+    @torch.no_grad()
+    def warmup_collectives(self):
+        """Allocate every large buffer of the streaming gradient path (both staging buffers, the gradient shards) and run one
+        reduce-scatter and one bf16 all-gather of the REAL sizes on the side stream, then synchronise.  Call it once, at a
+        quiescent point (all ranks aligned, no peer-memory kernels in flight): NCCL sets up the connections / algorithm of
+        a message size on first use, and the training path interleaves its collectives with spinning symmetric-memory
+        barrier kernels — first-use setup is kept away from that.  No-op for a single rank."""
+        if self.world == 1 or self._comm is None:
+            return
+        res = [u for u in self.units if u.kind == "resident"]
+        if not res:
+            return
+        big = max(u.n + u.pad for u in res)
+        dev = res[0].wflat.device
+        for k in range(2):
+            if self._stage[k] is None or self._stage[k].numel() < big:
+                self._stage[k] = torch.zeros(big, dtype=torch.float32, device=dev)
+        for u in res:
+            if u.gshard is None:
+                u.gshard = torch.empty(u.shard, dtype=torch.float32, device=dev)
+        u = max(res, key=lambda v: v.n)
+        torch.cuda.synchronize()
+        with torch.cuda.stream(self._comm):
+            tmp = torch.empty(u.shard, dtype=torch.float32, device=dev)
+            op = dist.ReduceOp.AVG if (self.average and self._nccl()) else dist.ReduceOp.SUM
+            dist.reduce_scatter_tensor(tmp, self._stage[0][:u.n + u.pad], op=op, group=self.group)
+            full16 = torch.empty(u.n + u.pad, dtype=torch.bfloat16, device=dev)
+            dist.all_gather_into_tensor(full16, u.my_slice(u.wflat).clone(), group=self.group)
+        torch.cuda.synchronize()
+        del tmp, full16
+
     # -- gradient intake ----------------------------------------------------------------------------
     def attach_hooks(self):
         """Move every flat unit's gradients into its flat fp32 gradient buffer as soon as autograd has accumulated them

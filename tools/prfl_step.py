@@ -33,12 +33,12 @@ def algorithmic_flops(L: int, i2v: bool, world: int):
     return (lin + att) / world, (2 * lin + 2.5 * att) / world
 
 
-def fit_blocks(world: int, L: int, want: int = 40, budget_gb: float = 138.0) -> int:
+def fit_blocks(world: int, L: int, want: int = 40, budget_gb: float = 135.0) -> int:
     """Largest VGM depth (<= want) whose training state fits `budget_gb` per GPU: bf16 resident weights + 1/W fp32
     master / moment shards + the per-block saved fp32 inputs (activation checkpointing) + one block's recompute stash."""
     per_block_params = 351.4e6 + 52.4e6
     M = L / world
-    fixed = 8 * per_block_params * 2 + 2 * per_block_params * 4 + 30 * M * 5120 * 2 + 8e9       # reward model, grad buffers, stash, slack
+    fixed = 8 * per_block_params * 2 + 2 * per_block_params * 4 + 50 * M * 5120 * 2 + 8e9       # reward model, grad buffers, one block's stash + backward temporaries, slack
     # bf16 resident + (master, m, v, grad shard) fp32 / W + saved fp32 block input + saved bf16 attention output (selective ckpt)
     per_block = per_block_params * (2 + 16.0 / world) + M * 5120 * 4 + M * 5120 * 2
     n = int((budget_gb * 1e9 - fixed) // per_block)
@@ -126,6 +126,10 @@ def measure(blocks: int, m_list=(2,), latent=LATENT_720P, steps: int = 2, i2v: b
                             "(FLOPs below count what is executed)" if engine.SAVE_ATTENTION else
                             "full: only the fp32 block input is kept (the reference's per-block activation checkpointing)",
            "runs": {}}
+    if optim is not None:
+        sync()
+        optim.warmup_collectives()                                  # big buffers + first-use NCCL setup at a quiescent point
+        sync()
     for _ in range(warmup):
         one_step(max(m_list))                                       # warm-up (operand caches, allocator, NCCL)
     sync()
