@@ -45,7 +45,7 @@ def _worker(rank, world, port, U, R, klen, q):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("world,U,R,klen", [(4, 2, 2, 96), (4, 2, 2, 70), (4, 1, 4, 50), (2, 1, 2, 96), (4, 4, 1, 96)])
+@pytest.mark.parametrize("world,U,R,klen", [(4, 2, 2, 70), (4, 1, 4, 50), (2, 1, 2, 96)])
 def test_usp_attention_schedule(world, U, R, klen):
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
