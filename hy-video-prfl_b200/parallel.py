@@ -304,7 +304,9 @@ class P2PUlysses:
          q/k/v : prfl_a2a_scatter_p2p — every rank stores its token chunk's heads straight into the owners' buffers
          out   : prfl_attn_fwd_p2p    — the attention epilogue stores each query row straight into its home rank
     with one cross-rank barrier after each (torch symmetric-memory signal pads).  Replaces 4 NCCL all-to-alls, the pack
-    and the unpack copies per block (communication.py:40-160 does 4 all_to_all_single + 8 transposes + 4 device syncs)."""
+    and the unpack copies per block (communication.py:40-160 does 4 all_to_all_single + 8 transposes + 4 device syncs).
+    The training path (recompute-forward + backward of a checkpointed block) uses the same buffers un-fused:
+    scatter_qkv / gather_out / scatter_grad / gather_grads below."""
 
     def __init__(self, L: int, H: int, device):
         import torch.distributed._symmetric_memory as symm_mem
