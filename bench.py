@@ -18,7 +18,11 @@ reward logit.
   prfl_step: the HEADLINE metric of BASELINE.json — "PRFL train s/step & DiT tokens/s, 14B 720P x 81f, 1/2/4/8 B200":
              train_step_refl-shaped step (tools/prfl_step.py) at L = 75 600, I2V architecture, Ulysses SP over the N ranks,
              sharded fp32 master / AdamW state, for m in {0, 2} no-grad denoising forwards; 40 blocks where the training
-             state fits (N >= 4), else the largest depth that fits, stated
+             state fits (N = 8), else the largest depth that fits with headroom, stated.  At N > 1 the leg runs in CHILD
+             processes with their own process group (`prfl_step_in_children`): a cross-rank hang cannot be cancelled from
+             inside a process, so the parents put a deadline on the children, kill exactly those PIDs, agree on the outcome
+             over their own (idle, healthy) group and retry once in a conservative mode (NCCL all-to-all exchange, no
+             side-stream overlap); `prfl_step.attempts` records what happened
   cpu_baseline : the oracle port (torch CPU fp32) timed on this box's host cores on the bounded sample (+ the GPU's
              throughput on that same sample, `gpu_same_sample`, for a like-for-like ratio)
   gpu_baseline : the same oracle port run on THIS GPU with eager PyTorch kernels — bf16 `F.linear` (cuBLAS), flash-attn 2
@@ -239,6 +243,122 @@ def gpu_eager_baseline(sd_dev, qa_dev, mlp_dev, x_dev, t_dev, ctx_dev, L, ours_m
                     "flash_attn_func (FA2 2.8), ATen LayerNorm / RMSNorm, float64 RoPE as the reference does — same workload, same weights",
             "ms_per_step": ms, "value": L / (ms * 1e-3), "unit": "tokens/s", "reward_logit": float(logit),
             "speedup_ours_over_eager": ms / ours_ms}
+
+
+# ---------------------------------------------------------------------------------------------------
+# N > 1: the PRFL training-step leg runs in CHILD processes (one per rank, their own process group)
+# ---------------------------------------------------------------------------------------------------
+# Why: a cross-rank hang inside a collective cannot be cancelled from inside the process — it wedges the NCCL communicator
+# of the job, costs the NCCL watchdog's ten minutes and ends in SIGABRT (profiles/r02_bench_n4_deadlock.log).  With the leg in
+# children, the parents (whose own process group stays healthy and idle) put a deadline on it, kill exactly the PIDs they
+# started, AGREE on the outcome over their own group, and can run the leg again in a more conservative mode.
+CHILD_MODES = [
+    ("default: peer-store Ulysses exchange, gradient reduce-scatter overlapped on a side stream", {}),
+    ("conservative: NCCL all-to-all exchange, reduce-scatter on the compute stream",
+     {"PRFL_ULYSSES": "nccl", "PRFL_RS": "serial"}),
+]
+
+
+def free_port():
+    import socket
+    with socket.socket(socket.AF_INET, socket.SOCK_STREAM) as sk:
+        sk.bind(("127.0.0.1", 0))
+        return sk.getsockname()[1]
+
+
+def child_env(rank, local, world, port, extra):
+    """Environment of one child rank: the launcher's variables with a rendezvous of the children's own (rank 0 of the
+    children hosts a fresh TCP store on `port`; torchrun's TORCHELASTIC_* variables would point them at the agent's store and
+    the parents' key space, so they are dropped)."""
+    env = {k: v for k, v in os.environ.items() if not k.startswith("TORCHELASTIC_")}
+    env.update(RANK=str(rank), LOCAL_RANK=str(local), WORLD_SIZE=str(world), LOCAL_WORLD_SIZE=str(world),
+               MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), PRFL_CHILD_OF=str(os.getpid()))
+    env.update(extra)
+    return env
+
+
+def wait_child(proc, deadline_s, fail_flag, tick=None):
+    """0 = exited with code 0; 1 = exited non-zero (or a peer's child did: `fail_flag` exists); 2 = still running at the
+    deadline.  In cases 1 / 2 the child — exactly the PID started here — is killed."""
+    t_end = time.time() + deadline_s
+    while True:
+        rc = proc.poll()
+        if rc is not None:
+            if rc != 0:
+                try:
+                    open(fail_flag, "w").close()                  # tell the other parents: their children wait for a dead peer
+                except OSError:
+                    pass
+            return 0 if rc == 0 else 1
+        crashed_elsewhere = os.path.exists(fail_flag)
+        if crashed_elsewhere or time.time() > t_end:
+            proc.kill()
+            proc.wait()
+            return 1 if crashed_elsewhere else 2
+        if tick:
+            tick()
+        time.sleep(0.5)
+
+
+def prfl_step_in_children(make_cmd, world, rank, local, dev, deadline_s, begin_leg=None, tick=None, modes=None):
+    """Run the leg as `world` child processes (this parent starts the one of its rank).  Collective over the parents'
+    default process group.  Returns (result or None, attempts, fallback_in_process):
+      * every child exits 0 -> rank 0 gets the result object its child wrote, the others get {};
+      * some child is still running at the deadline (a hang) -> all are killed and the next mode of `modes` is tried;
+      * some child exits non-zero (deterministic: out of memory, environment) -> no retry in another mode; the caller may run
+        the leg in-process (`fallback_in_process`)."""
+    import tempfile
+    import torch.distributed as dist
+    attempts = []
+    for name, extra in (modes or CHILD_MODES):
+        if begin_leg:
+            begin_leg(f"prfl_step in child processes ({name.split(':')[0]})")
+        port_t = torch.zeros(1, dtype=torch.int64, device=dev)
+        if rank == 0:
+            port_t[0] = free_port()
+        dist.broadcast(port_t, 0)
+        port = int(port_t)
+        base = os.path.join(tempfile.gettempdir(), f"prfl_step_{port}")
+        out, fail_flag, errf = base + ".json", base + ".failed", f"{base}.rank{rank}.err"
+        t0 = time.time()
+        with open(errf, "w") as ef:
+            proc = subprocess.Popen(make_cmd(out), env=child_env(rank, local, world, port, extra), stdout=subprocess.DEVNULL, stderr=ef,
+                                    cwd=ROOT)
+            st = wait_child(proc, deadline_s, fail_flag, tick)
+        flags = torch.tensor([int(st == 1), int(st == 2)], dtype=torch.int32, device=dev)
+        dist.all_reduce(flags, op=dist.ReduceOp.MAX)
+        crashed, hung = bool(int(flags[0])), bool(int(flags[1]))
+        att = {"mode": name, "seconds": round(time.time() - t0, 1),
+               "outcome": "ok" if not (crashed or hung) else ("a child exited non-zero" if crashed else f"no result within {deadline_s} s: children killed")}
+        res = None
+        if not crashed and not hung:
+            res = {}
+            if rank == 0:
+                try:
+                    res = json.load(open(out))
+                except Exception as e:
+                    att["outcome"], crashed = f"children exited 0 but the result is unreadable: {type(e).__name__}: {e}", True
+            ok_t = torch.tensor([0 if (rank == 0 and crashed) else 1], dtype=torch.int32, device=dev)
+            dist.broadcast(ok_t, 0)
+            if int(ok_t) == 0:
+                res, crashed = None, True
+        if res is None and rank == 0:
+            try:
+                att["stderr_tail_rank0"] = open(errf).read()[-400:]
+            except OSError:
+                pass
+        attempts.append(att)
+        for f in (errf, fail_flag if rank == 0 else None, out if rank == 0 else None):
+            try:
+                if f:
+                    os.remove(f)
+            except OSError:
+                pass
+        if res is not None:
+            return res, attempts, False
+        if crashed:
+            return None, attempts, True
+    return None, attempts, False
 
 
 # ---------------------------------------------------------------------------------------------------
@@ -466,7 +586,22 @@ def run_ours(args):
             import prfl_step
             Lp = 21 * 45 * 80
             blocks = args.prfl_blocks or prfl_step.fit_blocks(world, Lp)
-            prfl = prfl_step.measure(blocks, (0, 2), prfl_step.LATENT_720P, steps=args.prfl_steps, i2v=True, opt=True)
+            prfl, attempts, in_process = None, None, world == 1
+            if world > 1 and not args.prfl_in_process:
+                parallel._p2p_cache.clear()                          # the children need the memory; the parents stay idle meanwhile
+                gc.collect()
+                torch.cuda.empty_cache()
+                cmd = lambda out: [sys.executable, os.path.join(ROOT, "tools", "prfl_step.py"), "--blocks", str(blocks), "--nograd", "0,2",
+                                   "--steps", str(args.prfl_steps), "--out", out]
+                prfl, attempts, in_process = prfl_step_in_children(cmd, world, rank, local, dev, args.prfl_timeout, begin_leg,
+                                                                   tick=lambda: leg.__setitem__(1, time.time()))
+            if prfl is None and (in_process or args.prfl_in_process):
+                begin_leg("prfl_step (in process)")
+                prfl = prfl_step.measure(blocks, (0, 2), prfl_step.LATENT_720P, steps=args.prfl_steps, i2v=True, opt=True)
+            if prfl is None:
+                prfl = {"error": "the training-step leg did not finish in any mode (see attempts); the measurement above is unaffected"}
+            if attempts:
+                prfl["attempts"] = attempts
             prfl["metric"] = "PRFL train s/step (BASELINE.json headline), I2V 720Px81f, 14B dims"
             if blocks < 40:
                 prfl["note"] = (f"{blocks} of 40 VGM blocks: the largest depth whose bf16 weights + 1/{world} fp32 master/AdamW shards + "
@@ -482,7 +617,7 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
-if __name__ == "__main__":
+def build_parser():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
@@ -494,9 +629,15 @@ if __name__ == "__main__":
     ap.add_argument("--no-prfl", action="store_true", help="skip the PRFL 720P training-step leg")
     ap.add_argument("--prfl-blocks", type=int, default=0, help="VGM depth of the training-step leg (0 = the largest that fits)")
     ap.add_argument("--prfl-steps", type=int, default=2)
+    ap.add_argument("--prfl-timeout", type=int, default=210, help="N > 1: seconds one attempt of the training-step leg (child processes) may take")
+    ap.add_argument("--prfl-in-process", action="store_true", help="N > 1: run the training-step leg inside the bench processes (no children)")
     ap.add_argument("--leg-timeout", type=int, default=300, help="seconds any post-measurement leg may take before the line is "
                     "printed without it and the process exits (0 hangs are expected; this bounds the cost of one)")
-    a = ap.parse_args()
+    return ap
+
+
+if __name__ == "__main__":
+    a = build_parser().parse_args()
     if a.impl == "reference":
         run_reference(a)
     else:

@@ -33,6 +33,7 @@ result is produced with all_reduce + slice.
 from __future__ import annotations
 
 import math
+import os
 from typing import Dict, List, Optional, Sequence, Tuple
 
 import torch
@@ -302,7 +303,11 @@ class ShardedAdamW:
         self._stage_free: List[Optional[torch.cuda.Event]] = [None, None]
         self._stage_next = 0
         self._comm = None
-        if first.is_cuda and self.world > 1:
+        # PRFL_RS=serial keeps every collective of the gradient / parameter path on the compute stream (no side stream, no
+        # cross-stream events): nothing overlaps, and the order of work on each rank's single stream is the program order on
+        # every rank.  The conservative mode `bench.py` retries the training-step leg in if the overlapped mode hangs.
+        self.overlap = os.environ.get("PRFL_RS", "overlap").lower() != "serial"
+        if first.is_cuda and self.world > 1 and self.overlap:
             self._comm = torch.cuda.Stream(device=first.device)
 
     @torch.no_grad()
@@ -312,7 +317,7 @@ class ShardedAdamW:
         quiescent point (all ranks aligned, no peer-memory kernels in flight): NCCL sets up the connections / algorithm of
         a message size on first use, and the training path interleaves its collectives with spinning symmetric-memory
         barrier kernels — first-use setup is kept away from that.  No-op for a single rank."""
-        if self.world == 1 or self._comm is None:
+        if self.world == 1:
             return
         res = [u for u in self.units if u.kind == "resident"]
         if not res:
@@ -327,7 +332,7 @@ class ShardedAdamW:
                 u.gshard = torch.empty(u.shard, dtype=torch.float32, device=dev)
         u = max(res, key=lambda v: v.n)
         torch.cuda.synchronize()
-        with torch.cuda.stream(self._comm):
+        with torch.cuda.stream(self._comm if self._comm is not None else torch.cuda.current_stream()):
             tmp = torch.empty(u.shard, dtype=torch.float32, device=dev)
             op = dist.ReduceOp.AVG if (self.average and self._nccl()) else dist.ReduceOp.SUM
             dist.reduce_scatter_tensor(tmp, self._stage[0][:u.n + u.pad], op=op, group=self.group)
@@ -377,6 +382,9 @@ class ShardedAdamW:
     def _stage_release(self, u: ResidentUnit, buf: torch.Tensor, k: int):
         if self.world == 1:
             u.has_grad = True
+            return
+        if self._comm is None:                                 # PRFL_RS=serial: in stream order, nothing to wait for later
+            self._reduce_into_shard(u, buf)
             return
         ready = torch.cuda.Event()
         ready.record()

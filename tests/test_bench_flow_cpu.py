@@ -66,15 +66,7 @@ HARNESS = textwrap.dedent('''
     import bench
     bench.ClockSampler = lambda i: types.SimpleNamespace(stop=lambda a, b: {"sm_mhz": 1.0, "sm_max_mhz": 2.0, "reasons": []})
     sys.argv = ["bench.py", "--steps", "2", "--warmup", "1", "--leg-timeout", %r]
-    import argparse
-    ap = argparse.ArgumentParser()
-    for flag, typ, dflt in [("--gpus", int, 1), ("--steps", int, 5), ("--warmup", int, 3), ("--prfl-blocks", int, 0), ("--prfl-steps", int, 2),
-                            ("--leg-timeout", int, 300)]:
-        ap.add_argument(flag, type=typ, default=dflt)
-    ap.add_argument("--impl", default="ours")
-    for flag in ("--no-cpu", "--no-parity", "--no-gpu-baseline", "--no-prfl"):
-        ap.add_argument(flag, action="store_true")
-    bench.run_ours(ap.parse_args())
+    bench.run_ours(bench.build_parser().parse_args())
     print("CLEAN EXIT")
 ''')
 
@@ -113,3 +105,77 @@ def test_hanging_leg_trips_the_watchdog_line_still_printed_exit_code_zero():
     assert "CLEAN EXIT" not in res.stdout
     assert "did not finish within 3 s" in line["watchdog"] and "same_weights_14b" in line["watchdog"]
     assert line["value"] > 0 and line["prfl_step"] is None
+
+
+# ---------------------------------------------------------------------------------------------------
+# N > 1: the training-step leg in child processes (bench.prfl_step_in_children), 2 parents over gloo with fake children
+# ---------------------------------------------------------------------------------------------------
+CHILD = textwrap.dedent('''
+    import json, os, sys, time
+    out, scenario = sys.argv[1], sys.argv[2]
+    rank, serial = int(os.environ["RANK"]), os.environ.get("PRFL_RS") == "serial"
+    assert "TORCHELASTIC_USE_AGENT_STORE" not in os.environ and os.environ["MASTER_ADDR"] == "127.0.0.1"
+    if scenario == "hang_then_ok" and not serial:
+        time.sleep(3600)                                   # every rank of the first attempt waits for ever (a cross-rank deadlock)
+    if scenario == "crash" and rank == 1:
+        sys.exit(3)                                        # one rank dies; its peer would wait for it for ever
+    if scenario == "crash":
+        time.sleep(3600)
+    if rank == 0:
+        json.dump({"mode": os.environ.get("PRFL_ULYSSES", "p2p"), "port": os.environ["MASTER_PORT"], "world": os.environ["WORLD_SIZE"]},
+                  open(out, "w"))
+''')
+
+PARENT = textwrap.dedent('''
+    import json, os, sys, time
+    import torch, torch.distributed as dist
+    sys.path.insert(0, %r)
+    import bench
+    rank = int(os.environ["RANK"])
+    dist.init_process_group("gloo")
+    legs = []
+    res, attempts, in_process = bench.prfl_step_in_children(
+        lambda out: [sys.executable, "-c", %r, out, %r], 2, rank, rank, torch.device("cpu"), deadline_s=4, begin_leg=legs.append)
+    print("RESULT " + json.dumps({"rank": rank, "res": res, "attempts": attempts, "in_process": in_process, "legs": legs}), flush=True)
+    dist.barrier()                                         # the parents' own group is still healthy
+    dist.destroy_process_group()
+''')
+
+
+def _parents(scenario):
+    import socket
+    with socket.socket() as sk:
+        sk.bind(("127.0.0.1", 0))
+        port = sk.getsockname()[1]
+    procs = []
+    for r in range(2):
+        env = dict(os.environ, RANK=str(r), WORLD_SIZE="2", MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), OMP_NUM_THREADS="1",
+                   TORCHELASTIC_USE_AGENT_STORE="False", TORCHELASTIC_RUN_ID="x")      # what torchrun leaves in the environment
+        procs.append(subprocess.Popen([sys.executable, "-c", PARENT % (ROOT, CHILD, scenario)], env=env, stdout=subprocess.PIPE,
+                                      stderr=subprocess.PIPE, text=True, cwd=ROOT))
+    outs = []
+    for p in procs:
+        o, e = p.communicate(timeout=300)
+        assert p.returncode == 0, e[-3000:]
+        outs.append(json.loads([l for l in o.splitlines() if l.startswith("RESULT ")][0][7:]))
+    return sorted(outs, key=lambda d: d["rank"])
+
+
+def test_children_hang_is_killed_at_the_deadline_and_retried_in_the_conservative_mode():
+    t0 = __import__("time").time()
+    r0, r1 = _parents("hang_then_ok")
+    assert __import__("time").time() - t0 < 120
+    for r in (r0, r1):
+        assert [a["outcome"][:9] for a in r["attempts"]] == ["no result", "ok"], r["attempts"]
+        assert r["attempts"][1]["mode"].startswith("conservative") and r["in_process"] is False and len(r["legs"]) == 2
+    assert r0["res"]["mode"] == "nccl" and r0["res"]["world"] == "2" and r1["res"] == {}
+    assert r0["attempts"] == r1["attempts"] or [a["outcome"] for a in r0["attempts"]] == [a["outcome"] for a in r1["attempts"]]
+
+
+def test_children_crash_is_not_retried_and_peers_are_released_early():
+    t0 = __import__("time").time()
+    r0, r1 = _parents("crash")
+    for r in (r0, r1):
+        assert len(r["attempts"]) == 1 and r["attempts"][0]["outcome"] == "a child exited non-zero", r["attempts"]
+        assert r["res"] is None and r["in_process"] is True
+        assert r["attempts"][0]["seconds"] < 4                      # rank 0's child was killed when rank 1's died, not at the deadline

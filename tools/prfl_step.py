@@ -126,6 +126,11 @@ def measure(blocks: int, m_list=(2,), latent=LATENT_720P, steps: int = 2, i2v: b
                             "(FLOPs below count what is executed)" if engine.SAVE_ATTENTION else
                             "full: only the fp32 block input is kept (the reference's per-block activation checkpointing)",
            "runs": {}}
+    if world > 1:
+        from prfl_b200 import parallel
+        out["ulysses_exchange"] = "NCCL all_to_all_single (PRFL_ULYSSES=nccl)" if parallel._p2p_disabled else "peer stores into symmetric memory"
+        out["gradient_reduce_scatter"] = ("overlapped with the next block's backward on a side stream" if optim is not None and optim.overlap
+                                          else "on the compute stream (PRFL_RS=serial)")
     if optim is not None:
         sync()
         optim.warmup_collectives()                                  # big buffers + first-use NCCL setup at a quiescent point
@@ -172,6 +177,8 @@ def measure(blocks: int, m_list=(2,), latent=LATENT_720P, steps: int = 2, i2v: b
     if world > 1:
         dist.all_reduce(peak, op=dist.ReduceOp.MAX)
     out["peak_mem_gb"] = float(peak)
+    if world > 1 and parallel._p2p_disabled:                        # symmetric memory could not be set up: the run fell back
+        out["ulysses_exchange"] = "NCCL all_to_all_single"
     if profile:
         from torch.profiler import ProfilerActivity, profile as tprofile
         with tprofile(activities=[ProfilerActivity.CUDA]) as prof:
@@ -199,7 +206,18 @@ def main():
     ap.add_argument("--profile", action="store_true", help="one more step under torch.profiler -> per-kernel table")
     ap.add_argument("--no-opt", action="store_true")
     ap.add_argument("--legacy-fp32", action="store_true", help="round-1 layout: replicated fp32 parameters + bf16 operand caches")
+    ap.add_argument("--out", default="", help="rank 0 also writes the result object (one JSON document) to this file, atomically")
     args = ap.parse_args()
+    parent = os.environ.get("PRFL_CHILD_OF")
+    if parent:                                                      # started by bench.py: never outlive the bench process (an orphan would keep the GPU)
+        import ctypes
+        import signal
+        try:
+            ctypes.CDLL("libc.so.6", use_errno=True).prctl(1, int(signal.SIGKILL), 0, 0, 0)     # PR_SET_PDEATHSIG
+        except OSError:
+            pass
+        if os.getppid() != int(parent):
+            sys.exit(4)
     import torch.distributed as dist
     from prfl_b200 import parallel
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -215,6 +233,10 @@ def main():
                   args.profile, args.legacy_fp32)
     if int(os.environ.get("RANK", "0")) == 0:
         print(json.dumps(out, indent=1))
+        if args.out:
+            with open(args.out + ".tmp", "w") as f:
+                json.dump(out, f)
+            os.replace(args.out + ".tmp", args.out)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
