@@ -588,9 +588,8 @@ def run_ours(args):
             blocks = args.prfl_blocks or prfl_step.fit_blocks(world, Lp)
             prfl, attempts, in_process = None, None, world == 1
             if world > 1 and not args.prfl_in_process:
-                parallel._p2p_cache.clear()                          # the children need the memory; the parents stay idle meanwhile
-                gc.collect()
-                torch.cuda.empty_cache()
+                # the parents stay idle meanwhile; what they still hold (CUDA context, NCCL buffers, the small symmetric exchange
+                # buffers of the scoring step) is a few GB next to the children's <= 135 GB
                 cmd = lambda out: [sys.executable, os.path.join(ROOT, "tools", "prfl_step.py"), "--blocks", str(blocks), "--nograd", "0,2",
                                    "--steps", str(args.prfl_steps), "--out", out]
                 prfl, attempts, in_process = prfl_step_in_children(cmd, world, rank, local, dev, args.prfl_timeout, begin_leg,
