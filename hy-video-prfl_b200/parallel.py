@@ -312,6 +312,12 @@ class P2PUlysses:
         import torch.distributed._symmetric_memory as symm_mem
         self.P, self.rank = nccl_info.sp_size, nccl_info.rank_within_group
         self.L, self.H = L, H
+        # Set-up happens with the device DRAINED on every rank and is followed by a group-wide barrier (the unanimity
+        # all-reduce of get_p2p_ulysses): a peer's first signal must not be able to reach this rank's signal pads before their
+        # (stream-ordered) initialisation has executed here.  The one hang of round 2 (profiles/r02_bench_n4_deadlock.log)
+        # froze the devices right where the gradient buffer used to be created lazily in the middle of a backward — ~1000
+        # queued launches behind the host, and the only symmetric buffer whose creation was NOT followed by that barrier.
+        torch.cuda.synchronize(device)
         self.L_loc, self.Hl = L // self.P, H // self.P
         self.qkv = symm_mem.empty(4, L, self.Hl, 128, dtype=torch.bfloat16, device=device)      # slab 3: dO in the backward
         self.o = symm_mem.empty(self.L_loc, H, 128, dtype=torch.bfloat16, device=device)
@@ -325,6 +331,9 @@ class P2PUlysses:
         self.dqkv = symm_mem.empty(self.L_loc, 3 * H * 128, dtype=torch.bfloat16, device=device)
         self.h_dqkv = symm_mem.rendezvous(self.dqkv, nccl_info.group)
         self.dqkv_ptrs = [int(p) for p in self.h_dqkv.buffer_ptrs]
+        # every initialisation enqueued above has executed here before this rank joins the group-wide agreement in
+        # get_p2p_ulysses (an all-reduce + host read = a barrier): no rank can launch its first exchange earlier
+        torch.cuda.synchronize(device)
 
     def attention(self, q3: torch.Tensor, k3: torch.Tensor, v3: torch.Tensor, klen: int) -> torch.Tensor:
         """q3/k3/v3: local [L/P, H, 128] bf16 views.  Returns this rank's [L/P, H, 128] attention output (a view of the
@@ -391,7 +400,9 @@ def get_p2p_ulysses(L: int, H: int, device) -> Optional[P2PUlysses]:
         except Exception as e:  # no fabric / no peer access / out of memory on THIS rank
             err = e
         # the choice must be unanimous: a rank that fell back to NCCL while its peers wait in a symmetric-memory barrier
-        # would deadlock the group, so agree on the outcome (MIN over the SP group) before committing to either path
+        # would deadlock the group, so agree on the outcome (MIN over the SP group) before committing to either path.  The
+        # all-reduce + host read is also the barrier that ends the set-up: every rank has finished (and synchronised) its
+        # P2PUlysses.__init__ before any rank can launch its first exchange into a peer's buffers / signal pads
         ok = torch.tensor([0 if obj is None else 1], dtype=torch.int32, device=device)
         dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=nccl_info.group)
         if int(ok) == 0:
