@@ -582,11 +582,12 @@ def run_ours(args):
     if not args.no_prfl:
         begin_leg("prfl_step")
         sys.path.insert(0, os.path.join(ROOT, "tools"))
+        attempts = None
         try:
             import prfl_step
             Lp = 21 * 45 * 80
             blocks = args.prfl_blocks or prfl_step.fit_blocks(world, Lp)
-            prfl, attempts, in_process = None, None, world == 1
+            prfl, in_process = None, world == 1
             if world > 1 and not args.prfl_in_process:
                 # the parents stay idle meanwhile; what they still hold (CUDA context, NCCL buffers, the small symmetric exchange
                 # buffers of the scoring step) is a few GB next to the children's <= 135 GB
@@ -607,6 +608,8 @@ def run_ours(args):
                                 "checkpointed activations fit 180 GB at this N with headroom; per-block cost is depth-independent")
         except Exception as e:
             prfl = {"error": f"{type(e).__name__}: {str(e)[:400]}"}
+            if attempts:
+                prfl["attempts"] = attempts
         line["prfl_step"] = prfl
 
     begin_leg("teardown")

@@ -16,11 +16,15 @@ HARNESS = textwrap.dedent('''
     ROOT = %r
     sys.path.insert(0, ROOT)
     HANG = %r
+    EXTRA = %r
     # ---- fake device layer -------------------------------------------------------------------------
     class FakeEvent:
         def __init__(self, enable_timing=False): self.t = None
         def record(self, *a): self.t = time.time()
         def elapsed_time(self, other): return max((other.t - self.t) * 1e3, 1e-3)
+    import torch.distributed as dist
+    _real_init = dist.init_process_group
+    dist.init_process_group = lambda backend, device_id=None, **k: _real_init("gloo")      # N > 1 harness: gloo stands in for NCCL
     torch.cuda.is_available = lambda: True
     torch.cuda.set_device = lambda *a, **k: None
     torch.cuda.synchronize = lambda *a, **k: None
@@ -65,16 +69,18 @@ HARNESS = textwrap.dedent('''
     pkg._lib, pkg.ops, pkg.parallel = lib, ops, par
     import bench
     bench.ClockSampler = lambda i: types.SimpleNamespace(stop=lambda a, b: {"sm_mhz": 1.0, "sm_max_mhz": 2.0, "reasons": []})
-    sys.argv = ["bench.py", "--steps", "2", "--warmup", "1", "--leg-timeout", %r]
+    sys.argv = ["bench.py", "--steps", "2", "--warmup", "1", "--leg-timeout", %r] + EXTRA
     bench.run_ours(bench.build_parser().parse_args())
     print("CLEAN EXIT")
 ''')
 
 
-def _run(hang, leg_timeout):
-    code = HARNESS % (ROOT, hang, str(leg_timeout))
-    return subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=600, cwd=ROOT,
-                          env=dict(os.environ, OMP_NUM_THREADS="4"))
+def _run(hang, leg_timeout, extra=(), env=None, wait=True):
+    code = HARNESS % (ROOT, hang, list(extra), str(leg_timeout))
+    env = dict(os.environ, OMP_NUM_THREADS="4", **(env or {}))
+    if not wait:
+        return subprocess.Popen([sys.executable, "-c", code], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, cwd=ROOT, env=env)
+    return subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=600, cwd=ROOT, env=env)
 
 
 def _line(res):
@@ -179,3 +185,27 @@ def test_children_crash_is_not_retried_and_peers_are_released_early():
         assert len(r["attempts"]) == 1 and r["attempts"][0]["outcome"] == "a child exited non-zero", r["attempts"]
         assert r["res"] is None and r["in_process"] is True
         assert r["attempts"][0]["seconds"] < 4                      # rank 0's child was killed when rank 1's died, not at the deadline
+
+
+def test_two_rank_flow_children_crash_without_a_gpu_then_in_process_fallback_errors_and_rank0_prints_the_line():
+    """The N > 1 wiring of run_ours end to end (gloo standing in for NCCL, device layer faked): measurement, then the
+    training-step leg as REAL children (`tools/prfl_step.py`), which cannot start without a GPU -> a crash, agreed on by both
+    parents, no conservative retry, in-process fallback, whose failure becomes an error entry; exactly one line, from rank 0,
+    both ranks leave through the normal teardown (barrier + destroy_process_group on the parents' own group)."""
+    import socket
+    with socket.socket() as sk:
+        sk.bind(("127.0.0.1", 0))
+        port = sk.getsockname()[1]
+    procs = [_run(False, 300, extra=["--gpus", "2", "--no-parity", "--no-cpu", "--prfl-timeout", "120"], wait=False,
+                  env=dict(RANK=str(r), LOCAL_RANK=str(r), WORLD_SIZE="2", MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port)))
+             for r in range(2)]
+    outs = [p.communicate(timeout=600) for p in procs]
+    for p, (o, e) in zip(procs, outs):
+        assert p.returncode == 0 and "CLEAN EXIT" in o, (o[-1500:], e[-3000:])
+    lines0 = [l for l in outs[0][0].splitlines() if l.startswith("{")]
+    assert len(lines0) == 1 and not [l for l in outs[1][0].splitlines() if l.startswith("{")]
+    line = json.loads(lines0[0])
+    assert line["n_gpus"] == 2 and "watchdog" not in line and line["config"]["parallelism"] == "ulysses_sp2"
+    att = line["prfl_step"]["attempts"]
+    assert len(att) == 1 and att[0]["outcome"] == "a child exited non-zero" and att[0]["mode"].startswith("default")
+    assert "error" in line["prfl_step"]                          # the in-process fallback cannot run on the faked device either
