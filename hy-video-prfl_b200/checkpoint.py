@@ -22,7 +22,7 @@ from typing import Dict, Optional
 
 import torch
 
-__all__ = ["save_checkpoint", "load_state_dict", "save_optimizer", "load_optimizer"]
+__all__ = ["save_checkpoint", "write_model_dir", "load_model_dir", "load_state_dict", "save_optimizer", "load_optimizer"]
 
 MAX_SHARD_BYTES = 5 * 1024 ** 3
 
@@ -41,12 +41,19 @@ def save_checkpoint(transformer, rank: int, output_dir: str, step: int, ema: boo
     `ShardedAdamW.full_state_dict()` (the fp32 masters gathered from the 1/W shards, a collective every rank calls), which
     is what the reference's FSDP FULL_STATE_DICT gather yields (model_utils.py:75-86); without it the bf16 compute copies
     are written."""
-    from safetensors.torch import save_file
     if rank > 0:
         return None
     src = transformer.state_dict() if state_dict is None else state_dict
-    cpu_state = {k: v.detach().to("cpu").contiguous() for k, v in src.items()}
     save_dir = os.path.join(output_dir, f"checkpoint-{step}-ema" if ema else f"checkpoint-{step}")
+    write_model_dir(save_dir, src, _config_dict(transformer), max_bytes)
+    return save_dir
+
+
+def write_model_dir(save_dir: str, state: Dict[str, torch.Tensor], config: dict, max_bytes: int = MAX_SHARD_BYTES) -> None:
+    """The body of model_utils.py:88-126: one `diffusion_pytorch_model.safetensors` if the state is <= max_bytes, else greedy
+    shards over the sorted keys + index JSON; then `config.json`.  Shared by `save_checkpoint` and `WanModel.save_pretrained`."""
+    from safetensors.torch import save_file
+    cpu_state = {k: v.detach().to("cpu").contiguous() for k, v in state.items()}
     os.makedirs(save_dir, exist_ok=True)
     total_bytes = sum(v.numel() * v.element_size() for v in cpu_state.values())
     if total_bytes <= max_bytes:
@@ -70,8 +77,34 @@ def save_checkpoint(transformer, rank: int, output_dir: str, step: int, ema: boo
         with open(os.path.join(save_dir, "diffusion_pytorch_model.safetensors.index.json"), "w") as f:
             json.dump(index, f, indent=2)
     with open(os.path.join(save_dir, "config.json"), "w") as f:
-        json.dump(_config_dict(transformer), f, indent=4)
-    return save_dir
+        json.dump(config, f, indent=4)
+
+
+def load_model_dir(model_dir: str) -> Dict[str, torch.Tensor]:
+    """The weights of a `from_pretrained`-style directory (what diffusers' `ModelMixin.from_pretrained`, the loader behind the
+    reference's `WanModel.from_pretrained(...)` calls — train_prfl.py:182-217 — reads): the index JSON's shard list if there is
+    one, else `diffusion_pytorch_model.safetensors`, else the legacy `diffusion_pytorch_model.bin`.  Unlike `load_state_dict`
+    (the reference's merge-every-file helper) other `.safetensors` files in the directory are not touched."""
+    from safetensors.torch import load_file
+    idx = os.path.join(model_dir, "diffusion_pytorch_model.safetensors.index.json")
+    one = os.path.join(model_dir, "diffusion_pytorch_model.safetensors")
+    legacy = os.path.join(model_dir, "diffusion_pytorch_model.bin")
+    if os.path.exists(idx):
+        with open(idx) as f:
+            weight_map = json.load(f)["weight_map"]
+        state = {}
+        for name in sorted(set(weight_map.values())):
+            chunk = load_file(os.path.join(model_dir, name), device="cpu")
+            state.update(chunk)
+        missing = sorted(set(weight_map) - set(state))
+        if missing:
+            raise KeyError(f"{idx} lists {len(missing)} tensors its shards do not hold (first: {missing[0]})")
+        return state
+    if os.path.exists(one):
+        return load_file(one, device="cpu")
+    if os.path.exists(legacy):
+        return torch.load(legacy, map_location="cpu", weights_only=True)
+    raise FileNotFoundError(f"no diffusion_pytorch_model.safetensors[.index.json] / .bin under {model_dir}")
 
 
 def load_state_dict(model_dir: str, postfix: str = ".safetensors") -> Dict[str, torch.Tensor]:

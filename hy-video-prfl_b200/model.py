@@ -30,7 +30,7 @@ from . import ops
 from .parallel import get_sequence_parallel_state, nccl_info, ulysses_gather_tokens, ulysses_scatter_tokens, all_gather
 from .rope import rope_tables
 
-__all__ = ["WanModel", "PreparedContext", "WanAttentionBlock", "WanSelfAttention", "WanT2VCrossAttention", "WanI2VCrossAttention",
+__all__ = ["WanModel", "ModelConfig", "PreparedContext", "WanAttentionBlock", "WanSelfAttention", "WanT2VCrossAttention", "WanI2VCrossAttention",
            "WanRMSNorm", "WanLayerNorm", "Head", "MLPProj", "sinusoidal_embedding_1d", "rope_params", "rope_apply"]
 
 T5_CONTEXT_TOKEN_NUMBER = 512
@@ -450,6 +450,20 @@ class _UnpatchifyFn(torch.autograd.Function):
         return ops.unpatchify_bwd(dvid.detach().float().contiguous(), ctx.rows), None, None
 
 
+class ModelConfig(dict):
+    """`model.config` as the callers use it: a mapping (`dict(transformer.config)`, model_utils.py:119) whose entries are also
+    attributes, readable and assignable (`transformer.config.lora_rank = ...`, train_prfl.py:355-357)."""
+
+    def __getattr__(self, name):
+        try:
+            return self[name]
+        except KeyError:
+            raise AttributeError(name) from None
+
+    def __setattr__(self, name, value):
+        self[name] = value
+
+
 class WanModel(nn.Module):
     """model.py:413-729.  Drop-in: same __init__ / forward signature, attributes (`blocks`, `head`, `freqs`,
     `enable_teacache`, `_no_split_modules`, `config`) and state-dict keys."""
@@ -464,10 +478,10 @@ class WanModel(nn.Module):
         super().__init__()
         assert model_type in ["t2v", "i2v", "flf2v"]
         assert tuple(patch_size) == (1, 2, 2), "prfl_b200 patchify kernels implement patch_size (1, 2, 2)"
-        self.config = dict(model_type=model_type, patch_size=tuple(patch_size), text_len=text_len, in_dim=in_dim, dim=dim,
-                           ffn_dim=ffn_dim, freq_dim=freq_dim, text_dim=text_dim, out_dim=out_dim, num_heads=num_heads,
-                           num_layers=num_layers, window_size=tuple(window_size), qk_norm=qk_norm,
-                           cross_attn_norm=cross_attn_norm, eps=eps)
+        self.config = ModelConfig(model_type=model_type, patch_size=tuple(patch_size), text_len=text_len, in_dim=in_dim, dim=dim,
+                                  ffn_dim=ffn_dim, freq_dim=freq_dim, text_dim=text_dim, out_dim=out_dim, num_heads=num_heads,
+                                  num_layers=num_layers, window_size=tuple(window_size), qk_norm=qk_norm,
+                                  cross_attn_norm=cross_attn_norm, eps=eps)
         self.model_type = model_type
         self.patch_size = tuple(patch_size)
         self.text_len = text_len
@@ -647,8 +661,52 @@ class WanModel(nn.Module):
                 nn.init.normal_(m.weight, std=.02)
         nn.init.zeros_(self.head.head.weight)
 
+    _CONFIG_KEYS = ("model_type", "patch_size", "text_len", "in_dim", "dim", "ffn_dim", "freq_dim", "text_dim", "out_dim",
+                    "num_heads", "num_layers", "window_size", "qk_norm", "cross_attn_norm", "eps")
+
     @classmethod
     def from_config(cls, config):
-        keys = ("model_type", "patch_size", "text_len", "in_dim", "dim", "ffn_dim", "freq_dim", "text_dim", "out_dim",
-                "num_heads", "num_layers", "window_size", "qk_norm", "cross_attn_norm", "eps")
-        return cls(**{k: config[k] for k in keys if k in config})
+        """`ModelMixin.from_config` as the trainers use it (train_prfl.py:205): a dict (a parsed config.json) -> a randomly
+        initialised model.  Keys that are not constructor arguments (`_class_name`, `_diffusers_version`, `dtype`, LoRA
+        annotations) are ignored; constructor arguments the file omits (the reference's `ignore_for_config` list) take
+        their defaults."""
+        return cls(**{k: config[k] for k in cls._CONFIG_KEYS if k in config})
+
+    @classmethod
+    def from_pretrained(cls, pretrained_model_name_or_path, subfolder=None, torch_dtype=None, strict=True, **unused):
+        """`WanModel.from_pretrained(dir)` — how every reference trainer and pipeline obtains the model (train_prfl.py:182-217,
+        train_pavrm.py:170-181, inference_pavrm.py:171-182, text2video.py; diffusers' `ModelMixin.from_pretrained` in the
+        reference): `config.json` -> `from_config`, weights from `diffusion_pytorch_model.safetensors` or its sharded form
+        (the layout `checkpoint.save_checkpoint` and the reference's `save_checkpoint` write), strict key match, `eval()`.
+        A local directory only (no hub); `torch_dtype` casts the floating-point parameters after loading.  With
+        `strict=False` returns `(model, missing_keys, unexpected_keys)`."""
+        import json
+        import os
+        from .checkpoint import load_model_dir
+        path = str(pretrained_model_name_or_path)
+        if subfolder:
+            path = os.path.join(path, subfolder)
+        cfg_path = os.path.join(path, "config.json")
+        if not os.path.isfile(cfg_path):
+            raise FileNotFoundError(f"{cfg_path} not found: from_pretrained takes a local checkpoint directory")
+        with open(cfg_path) as f:
+            config = json.load(f)
+        model = cls.from_config(config)
+        extra = {k: v for k, v in config.items() if k not in cls._CONFIG_KEYS and not k.startswith("_")}
+        model.config.update(extra)                                   # e.g. lora_rank annotations survive a save / load cycle
+        state = load_model_dir(path)
+        missing, unexpected = model.load_state_dict(state, strict=False)
+        if strict and (missing or unexpected):
+            raise RuntimeError(f"{path}: state dict does not match {cls.__name__}({ {k: config.get(k) for k in ('model_type', 'dim', 'num_layers')} }): "
+                               f"{len(missing)} missing (first: {missing[:3]}), {len(unexpected)} unexpected (first: {unexpected[:3]})")
+        if torch_dtype is not None:
+            model = model.to(torch_dtype)
+        model.eval()
+        return model if strict else (model, list(missing), list(unexpected))
+
+    def save_pretrained(self, save_directory, max_shard_size: int = 5 * 1024 ** 3, state_dict=None):
+        """Write `save_directory/{config.json, diffusion_pytorch_model*.safetensors[, index]}` — the directory
+        `from_pretrained` (this one and the reference's) reads.  `state_dict`: see `checkpoint.save_checkpoint`."""
+        from .checkpoint import _config_dict, write_model_dir
+        cfg = {"_class_name": type(self).__name__, **_config_dict(self)}
+        write_model_dir(str(save_directory), self.state_dict() if state_dict is None else state_dict, cfg, max_shard_size)

@@ -43,3 +43,16 @@ def test_prfl_step_depth_rule():
     assert d[3] == 40 and 1 <= d[0] < d[1] < d[2] <= 40
     f8, b8 = prfl_step.algorithmic_flops(L, True, 8)
     assert abs(f8 * 8 / 163.08e12 - 1) < 0.02                            # 163.08 TFLOP per 720P block forward (+CLIP tokens)
+
+
+def test_prfl_step_extrapolation_in_m():
+    """s/step is affine in the number of no-grad forwards: m19 (= E[m] of the reference's randint(0, 38)) and m38 follow from
+    two measured m; nothing is reported from a single m."""
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import prfl_step
+    n8 = json.load(open(os.path.join(ROOT, "profiles", "r02_bench_n8.json")))["prfl_step"]["runs"]
+    ex = prfl_step.extrapolate_m(n8)["extrapolated_s_per_step"]
+    s0, s2 = n8["m0"]["s_per_step"], n8["m2"]["s_per_step"]
+    assert abs(ex["per_nograd_forward_s"] - (s2 - s0) / 2) < 1e-12 and abs(ex["m0"] - s0) < 1e-12
+    assert abs(ex["m19"] - (s0 + 19 * (s2 - s0) / 2)) < 1e-9 and 16.0 < ex["m19"] < 17.5 and ex["m38"] > ex["m19"]
+    assert prfl_step.extrapolate_m({"m2": {"s_per_step": 5.0}}) == {}

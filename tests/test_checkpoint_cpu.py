@@ -103,3 +103,62 @@ def test_optimizer_shard_roundtrip(tmp_path):
     run(b, ob, 2, 6)
     for pa, pb in zip(a.parameters(), b.parameters()):
         assert torch.equal(pa, pb)                                   # resumed run == uninterrupted run, bit for bit
+
+
+def test_from_pretrained_reads_what_save_checkpoint_writes(tmp_path):
+    """`WanModel.from_pretrained(dir)` is how every reference trainer obtains its models (train_prfl.py:182-217); the directory
+    it reads is the one `save_checkpoint` writes (single file and sharded), plus published Wan2.1-style config files that omit
+    the constructor arguments the reference lists in `ignore_for_config` and carry `_class_name` / `_diffusers_version`."""
+    import pytest
+    from prfl_b200.checkpoint import save_checkpoint
+    from prfl_b200.model import WanModel
+    m, cfg = _tiny()
+    sd = m.state_dict()
+    for kw in ({}, {"max_bytes": 600_000}):                                  # one file / index + shards
+        d = save_checkpoint(m, 0, str(tmp_path / ("s" if kw else "o")), 11, **kw)
+        # an optimizer shard in the same directory is not a weight file
+        torch.save({}, os.path.join(d, "scratch.bin"))
+        b = WanModel.from_pretrained(d)
+        assert not b.training and dict(b.config) == {k: v for k, v in m.config.items() if k != "dtype"}
+        got = b.state_dict()
+        assert set(got) == set(sd) and all(torch.equal(got[k], sd[k]) for k in sd)
+    # a published-style config.json: ignored keys absent, bookkeeping keys present, an annotation the trainers add
+    ignored = ("patch_size", "cross_attn_norm", "qk_norm", "text_dim", "window_size")
+    full = json.load(open(os.path.join(d, "config.json")))
+    slim = {k: v for k, v in full.items() if k not in ignored} | {"_class_name": "WanModel", "_diffusers_version": "0.30.0", "lora_rank": 4}
+    # text_dim is not the default in the tiny model: keep it (a real 14B config relies on the default 4096)
+    slim["text_dim"] = full["text_dim"]
+    json.dump(slim, open(os.path.join(d, "config.json"), "w"))
+    c = WanModel.from_pretrained(str(tmp_path / "s"), subfolder="checkpoint-11", torch_dtype=torch.bfloat16)
+    assert c.config.lora_rank == 4 and c.config["patch_size"] == (1, 2, 2) and "_class_name" not in c.config
+    assert c.blocks[0].ffn[0].weight.dtype == torch.bfloat16
+    assert torch.equal(c.blocks[0].ffn[0].weight, sd["blocks.0.ffn.0.weight"].bfloat16())
+    c.config.lora_alpha = 8                                                  # train_prfl.py:355-357 assigns attributes
+    assert dict(c.config)["lora_alpha"] == 8
+    # strict by default; strict=False reports like load_state_dict (train_prfl.py:209 uses the non-strict form by hand)
+    from safetensors.torch import load_file, save_file
+    one = str(tmp_path / "o" / "checkpoint-11")
+    st = load_file(os.path.join(one, "diffusion_pytorch_model.safetensors"))
+    st.pop("blocks.1.modulation")
+    st["not.a.key"] = torch.zeros(1)
+    save_file(st, os.path.join(one, "diffusion_pytorch_model.safetensors"))
+    with pytest.raises(RuntimeError, match="1 missing.*1 unexpected"):
+        WanModel.from_pretrained(one)
+    _, missing, unexpected = WanModel.from_pretrained(one, strict=False)
+    assert missing == ["blocks.1.modulation"] and unexpected == ["not.a.key"]
+    with pytest.raises(FileNotFoundError):
+        WanModel.from_pretrained(str(tmp_path / "nowhere"))
+
+
+def test_save_pretrained_roundtrip_and_reference_loader(tmp_path):
+    """save_pretrained -> from_pretrained, and the reference's own `load_state_dict(model_dir)` (model_utils.py:128-141, restated
+    in checkpoint.load_state_dict) reads the same directory."""
+    from prfl_b200.checkpoint import load_state_dict
+    from prfl_b200.model import WanModel
+    m, _ = _tiny()
+    m.save_pretrained(tmp_path / "p", max_shard_size=600_000)
+    cfg = json.load(open(tmp_path / "p" / "config.json"))
+    assert cfg["_class_name"] == "WanModel" and "dtype" not in cfg and cfg["dim"] == m.config["dim"]
+    b = WanModel.from_pretrained(tmp_path / "p")
+    sd, back = m.state_dict(), load_state_dict(str(tmp_path / "p"))
+    assert all(torch.equal(b.state_dict()[k], sd[k]) and torch.equal(back[k], sd[k]) for k in sd)

@@ -136,6 +136,9 @@ def test_resident_block_without_optimizer_refuses_weight_grads():
         out.sum().backward()
 
 
+@pytest.mark.xfail(strict=False, reason="written after this round's GPU budget was spent: never executed on hardware (the oracle half "
+                   "runs on CPU; the kernels it drives are covered by the B = 1 tests above). XPASS = it holds; a failure here "
+                   "must not stop the `-x` run of the verified tests")
 def test_ragged_batch_backward_sink_equals_autograd_and_oracle():
     """B = 2 samples of different sizes (300 and 105 tokens, zero-padded to 320): the per-sample loop of BlockFn.backward
     accumulates the second sample's weight gradients onto the first's (`beta` in the wgrad GEMMs of the sink path, `+` in
