@@ -114,6 +114,14 @@ def initialize_sequence_parallel_group(sequence_parallel_size: int):
             nccl_info.group_id = i
 
 
+def destroy_sequence_parallel_group():
+    """parallel_states.py:127-129 (+ the peer-mapped exchange buffers of this group are released first)."""
+    global _SEQUENCE_PARALLEL_STATE
+    _p2p_cache.clear()
+    _SEQUENCE_PARALLEL_STATE = False
+    dist.destroy_process_group()
+
+
 def broadcast(input_: torch.Tensor):
     """communication.py:17-19."""
     src = nccl_info.group_id * nccl_info.sp_size

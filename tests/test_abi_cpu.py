@@ -91,3 +91,33 @@ def test_attention_split_policy():
                 if tail:
                     per = -(-n_kv // pieces)
                     assert 2 <= pieces <= 4 and 2 * tail <= 148 and (pieces - 1) * per < n_kv      # no empty piece
+
+
+def test_python_surface_the_reference_callers_import():
+    """Every name the reference trainers / pipelines import from the modules this package replaces (train_prfl.py:28-31,
+    41-58, 97; train_pavrm.py:37-52; inference_prfl.py:71-82) exists here with the reference's call signature."""
+    import inspect
+    from prfl_b200 import checkpoint, model, network, parallel, scheduler
+    for mod, names in ((model, ("WanModel", "WanAttentionBlock", "WanSelfAttention", "WanT2VCrossAttention", "WanI2VCrossAttention",
+                                "WanRMSNorm", "WanLayerNorm", "Head", "MLPProj", "sinusoidal_embedding_1d", "rope_params", "rope_apply")),
+                       (network, ("MLP", "QueryAttention", "forward_mlp", "forward_siamese")),
+                       (parallel, ("nccl_info", "COMM_INFO", "initialize_sequence_parallel_state", "initialize_sequence_parallel_group",
+                                   "set_sequence_parallel_state", "get_sequence_parallel_state", "destroy_sequence_parallel_group",
+                                   "broadcast", "all_gather", "all_to_all_4D", "SeqAllToAll4D", "initialize_usp_state")),
+                       (scheduler, ("FlowUniPCMultistepScheduler",)),
+                       (checkpoint, ("save_checkpoint", "load_state_dict"))):
+        for n in names:
+            assert hasattr(mod, n), (mod.__name__, n)
+    sig = lambda f: list(inspect.signature(f).parameters)
+    assert sig(model.WanModel.forward)[:10] == ["self", "x", "t", "context", "seq_len", "clip_fea", "y", "cond_flag", "output_features",
+                                                "selected_layers"]
+    assert sig(model.WanModel.__init__)[1:] == ["model_type", "patch_size", "text_len", "in_dim", "dim", "ffn_dim", "freq_dim", "text_dim",
+                                                "out_dim", "num_heads", "num_layers", "window_size", "qk_norm", "cross_attn_norm", "eps"]
+    assert sig(model.WanAttentionBlock.forward)[:8] == ["self", "x", "e", "seq_lens", "grid_sizes", "freqs", "context", "context_lens"]
+    assert sig(network.QueryAttention.__init__)[1:] == ["feature_dim", "num_queries", "num_heads", "dropout", "layer_norm", "return_type",
+                                                       "product_text", "text_dim"]
+    assert sig(network.QueryAttention.forward)[:4] == ["self", "x", "e", "text"]
+    assert sig(parallel.all_to_all_4D) == ["input_", "scatter_dim", "gather_dim"] and sig(parallel.all_gather) == ["input_", "dim"]
+    assert sig(checkpoint.save_checkpoint)[:5] == ["transformer", "rank", "output_dir", "step", "ema"]
+    for cm in ("from_pretrained", "from_config", "save_pretrained"):
+        assert callable(getattr(model.WanModel, cm))
