@@ -5,7 +5,7 @@ during warm-up at N > 1 (the driver's GPU test box has one GPU), printing the nu
 Checks, on every rank:
   sp_fwd        noise prediction + gathered features vs the oracle (cos >= 0.999, max-rel <= 2e-2); reward logit
                 (sp-local pooling == gathered pooling to 1e-5, vs oracle within 1e-2)
-  sp_bwd        through the NCCL all-to-all path: the SUM over SP ranks of the partial weight / input gradients equals
+  sp_bwd        through the training-path exchanges (peer stores; NCCL all-to-all under PRFL_ULYSSES=nccl): the SUM over SP ranks of the partial weight / input gradients equals
                 the oracle's SP=1 gradient, same tolerances
   sharded_adamw `ShardedAdamW` (resident bf16 weights, reduce-scattered fp32 gradient shards, 1/W fp32 masters,
                 bf16 all-gather) vs dense torch.optim.AdamW on the replicated fp32 model, 2 steps with clip_grad_norm_(1.0):
@@ -37,6 +37,7 @@ COS_MIN, REL_MAX, LOGIT_TOL, ADAMW_REL, GRAD_REL = 0.999, 2e-2, 1e-2, 2e-6, 1e-5
 
 def run_checks(world: int, rank: int, verbose: bool = True) -> dict:
     """Requires an initialised NCCL process group + `parallel.initialize_sequence_parallel_state(world)`."""
+    from prfl_b200 import parallel as _parallel
     from prfl_b200.model import WanModel
     from prfl_b200.pavrm import PavrmScorer
     from prfl_b200.sharding import ShardedAdamW
@@ -85,7 +86,8 @@ def run_checks(world: int, rank: int, verbose: bool = True) -> dict:
         if rank == 0:
             say(f"  sum-over-ranks grad {k}: cos={c:.6f} rel={r:.4f}")
     res["sp_bwd"] = {"cos": worst_c, "max_rel": worst_r, "ok": bool(worst_c >= COS_MIN and worst_r <= REL_MAX),
-                     "what": "worst over grad_x + 7 weight grads, sum over SP ranks vs oracle SP=1 (NCCL all-to-all path)"}
+                     "what": "worst over grad_x + 7 weight grads, sum over SP ranks vs oracle SP=1 (training exchanges: "
+                             + ("NCCL all-to-all" if _parallel._p2p_disabled else "peer stores into symmetric memory") + ")"}
     m.zero_grad(set_to_none=True)
 
     with torch.no_grad():
