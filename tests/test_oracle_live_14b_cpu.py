@@ -54,3 +54,32 @@ def test_oracle_equals_live_reference_at_14b_dims(mt):
     assert out[0].shape == ref_out.shape == (16, 2, 12, 20)
     bad = {k: v for k, v in report.items() if not (v[0] > 1 - 1e-6 and v[1] < (2e-5 if k == "out" else 1e-4))}
     assert not bad, bad
+
+
+@pytest.mark.parametrize("n_sel", [1, 2])
+def test_reward_head_oracle_equals_live_reference_at_dim_5120(n_sel):
+    """QueryAttention (1 learnable query, 8 heads of 640) + MLP at the 14B feature width, on [n_sel, B, L, C] features
+    (n_sel = 2 is the trainers' default `feature_layer: [6, 7]`, train_prfl.py:233-235): pooled vector, reward logit and the
+    gradient that flows back into the features."""
+    torch.set_num_threads(8)
+    _, N = ref_shim.load()
+    qa_sd, mlp_sd = synth.make_reward_state_dicts(5120, 81)
+    g = torch.Generator().manual_seed(82)
+    feats = torch.randn(n_sel, 1, 150, 5120, generator=g)
+    qa = N.QueryAttention(5120, num_queries=1, num_heads=8, dropout=0.0, return_type="query").eval()
+    qa.load_state_dict(qa_sd, strict=True)
+    mlp = N.MLP(5120).eval()
+    mlp.load_state_dict(mlp_sd, strict=True)
+    fr = feats.clone().requires_grad_(True)
+    pooled_r = qa(fr)
+    prob_r = N.forward_mlp(mlp, pooled_r)
+    prob_r.sum().backward()
+    fo = feats.clone().requires_grad_(True)
+    pooled_o = O.query_attention(qa_sd, fo, 8, "query")
+    logit_o = O.reward_mlp(mlp_sd, pooled_o)
+    torch.sigmoid(logit_o).sum().backward()
+    # `output + queries` broadcasts [B, C] + [n_sel * B, 1, C] (network.py:103-104, SURVEY Appendix B item 9): n_sel identical rows
+    assert pooled_o.shape == pooled_r.shape == (n_sel, 1, 5120) and logit_o.shape == prob_r.shape == (n_sel, 1, 1)
+    for name, a, b, tol in (("pooled", pooled_o, pooled_r, 2e-5), ("logit", logit_o, mlp(pooled_r), 2e-5), ("grad", fo.grad, fr.grad, 1e-4)):
+        c, r = cos_rel(a, b)
+        assert c > 1 - 1e-6 and r < tol, (name, c, r)
