@@ -121,3 +121,29 @@ def test_python_surface_the_reference_callers_import():
     assert sig(checkpoint.save_checkpoint)[:5] == ["transformer", "rank", "output_dir", "step", "ema"]
     for cm in ("from_pretrained", "from_config", "save_pretrained"):
         assert callable(getattr(model.WanModel, cm))
+
+
+def test_header_is_plain_c_and_links_from_a_c_host(tmp_path):
+    """The boundary is a C ABI: `include/prfl_b200.h` compiles as strict C99 (`-pedantic -Werror`: no C++-isms, no torch or CUDA
+    runtime types in a signature) and a C program links the shared library and calls it.  Without a GPU the call must come back
+    with an error code and a message — never compute anything."""
+    import shutil
+    import subprocess
+    from prfl_b200 import _lib
+    if shutil.which("gcc") is None:
+        pytest.skip("no gcc")
+    src = tmp_path / "host.c"
+    src.write_text('#include <stdio.h>\n#include "prfl_b200.h"\n'
+                   "int main(void) {\n"
+                   "  int rc = prfl_cast_f32_bf16(NULL, NULL, 0, NULL);\n"
+                   '  printf("%d %d %s\\n", prfl_abi_version(), rc, prfl_last_error_string());\n'
+                   "  return 0;\n}\n")
+    exe = tmp_path / "host"
+    libdir = os.path.dirname(_lib.LIB_PATH)
+    res = subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-Werror", "-pedantic", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe),
+                          "-L", libdir, "-lprfl_b200", f"-Wl,-rpath,{libdir}"], capture_output=True, text=True)
+    assert res.returncode == 0, res.stderr[-2000:]
+    out = subprocess.run([str(exe)], capture_output=True, text=True, timeout=120).stdout.split(" ", 2)
+    assert out[0] == "2"
+    if not torch.cuda.is_available():
+        assert out[1] == "-3" and "no CPU fallback" in out[2]
