@@ -194,6 +194,8 @@ class WanSelfAttention(nn.Module):
         self.num_heads = num_heads
         self.head_dim = dim // num_heads
         assert self.head_dim == 128, "prfl_b200 attention kernels are head_dim 128 only"
+        if tuple(window_size) != (-1, -1):      # every shipped config (wan/configs/*.py) uses the global window; refuse rather than differ
+            raise NotImplementedError(f"window_size={tuple(window_size)}: the attention kernels implement global attention only")
         self.window_size = window_size
         self.qk_norm = qk_norm
         self.eps = eps

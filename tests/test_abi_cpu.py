@@ -147,3 +147,22 @@ def test_header_is_plain_c_and_links_from_a_c_host(tmp_path):
     assert out[0] == "2"
     if not torch.cuda.is_available():
         assert out[1] == "-3" and "no CPU fallback" in out[2]
+
+
+def test_off_path_options_are_refused_not_silently_ignored():
+    """Options the kernels do not implement raise at construction / call time (no silent difference from the reference)."""
+    from prfl_b200.attention import flash_attention
+    from prfl_b200.model import WanModel, WanSelfAttention
+    from prfl_b200.network import QueryAttention
+    with pytest.raises(NotImplementedError):
+        WanSelfAttention(256, 2, window_size=(128, 128))
+    with pytest.raises(AssertionError):
+        WanSelfAttention(192, 2)                                        # head_dim 96
+    with pytest.raises(AssertionError):
+        WanModel(patch_size=(1, 4, 4), dim=256, ffn_dim=512, num_heads=2, num_layers=1)
+    with pytest.raises(AssertionError):
+        QueryAttention(256, num_queries=2)
+    q = torch.zeros(1, 4, 2, 128)
+    for kw in (dict(causal=True), dict(dropout_p=0.1), dict(window_size=(4, 4)), dict(q_lens=torch.tensor([4]))):
+        with pytest.raises(NotImplementedError):
+            flash_attention(q, q, q, **kw)
