@@ -37,6 +37,7 @@ class COMM_INFO:
 
 nccl_info = COMM_INFO()
 _SEQUENCE_PARALLEL_STATE = False
+_adopted = [False]            # True while the state above mirrors the reference's own bookkeeping (adopt_reference_state)
 
 
 def initialize_sequence_parallel_state(sequence_parallel_size: int):
@@ -112,6 +113,41 @@ def initialize_sequence_parallel_group(sequence_parallel_size: int):
             nccl_info.group = group
             nccl_info.rank_within_group = rank - i * sequence_parallel_size
             nccl_info.group_id = i
+
+
+def adopt_reference_state(ref_states=None) -> bool:
+    """`plugin.install()` patches the blocks of a REFERENCE model, whose trainer initialised the reference's own bookkeeping
+    (`diffusers_lite.utils.parallel_states`: `initialize_sequence_parallel_state`, train_prfl.py:119) — not this module's.  The
+    patched blocks read THIS module's state, so mirror the reference's (flag, SP group, sizes, ranks) into it whenever the two
+    differ; without this a patched model would silently run its self-attention without the Ulysses exchange.  Returns True if
+    something was adopted.  No-op when the reference module is not loaded in this process."""
+    global _SEQUENCE_PARALLEL_STATE
+    import sys
+    mod = ref_states if ref_states is not None else sys.modules.get("diffusers_lite.utils.parallel_states")
+    if mod is None or mod is sys.modules.get(__name__):
+        return False
+    info = getattr(mod, "nccl_info", None)
+    if info is None or not hasattr(mod, "get_sequence_parallel_state"):
+        return False
+    on = bool(mod.get_sequence_parallel_state()) and int(getattr(info, "sp_size", 1)) > 1
+    if not on and not _adopted[0]:
+        return False                                             # this module's state was set natively (class-swap route): not ours to undo
+    same = (on == _SEQUENCE_PARALLEL_STATE) and (not on or (info.group is nccl_info.group and info.sp_size == nccl_info.sp_size and
+                                                           info.rank_within_group == nccl_info.rank_within_group))
+    if same:
+        return False
+    _adopted[0] = on
+    _p2p_cache.clear()                                           # peer buffers belong to the previous group
+    _SEQUENCE_PARALLEL_STATE = on
+    nccl_info.group = info.group if on else None
+    nccl_info.sp_size = int(info.sp_size) if on else 1
+    nccl_info.global_rank = int(info.global_rank)
+    nccl_info.rank_within_group = int(info.rank_within_group) if on else 0
+    nccl_info.group_id = int(info.group_id)
+    nccl_info.ulysses_group, nccl_info.ring_group = nccl_info.group, None
+    nccl_info.ulysses_degree, nccl_info.ring_degree = nccl_info.sp_size, 1
+    nccl_info.ulysses_rank, nccl_info.ring_rank, nccl_info.ring_ranks = nccl_info.rank_within_group, 0, ()
+    return True
 
 
 def destroy_sequence_parallel_group():

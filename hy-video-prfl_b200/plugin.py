@@ -20,6 +20,7 @@ import torch
 import torch.nn as nn
 
 from .model import WanAttentionBlock
+from .parallel import adopt_reference_state
 
 __all__ = ["install", "uninstall"]
 
@@ -58,6 +59,10 @@ def install(ref_model: nn.Module) -> nn.Module:
         def forward(x, e, seq_lens, grid_sizes, freqs, context, context_lens, _blk=blk, _fast=fast, _first=(i == 0)):
             if not _blk._prfl_b200_on:
                 return _blk.old_forward(x, e, seq_lens, grid_sizes, freqs, context, context_lens)
+            if _first:
+                # the reference model chunks the tokens by ITS sequence-parallel state (model.py:618-619); the patched blocks must
+                # exchange by the same one (checked once per forward, at block 0: a dict lookup and a few comparisons)
+                adopt_reference_state()
             # the reference feeds block 0 the bf16 patch embedding (model.py:345 with x.dtype == bf16): keep that rounding
             return _fast(x.float().contiguous(), e, seq_lens, grid_sizes, freqs, context, context_lens,
                          first_block_bf16_input=_first and x.dtype == torch.bfloat16)
@@ -68,6 +73,7 @@ def install(ref_model: nn.Module) -> nn.Module:
             if hasattr(b, "_prfl_b200_fast"):
                 b._prfl_b200_on = bool(flag)
     ref_model.prfl_b200_enable = enable
+    adopt_reference_state()
     return ref_model
 
 

@@ -47,3 +47,36 @@ def test_install_on_real_reference_model(mt):
         with pytest.raises(PrflError):
             with torch.no_grad():
                 ref(inp["x"], t=inp["t"], context=inp["context"], seq_len=inp["seq_len"], **kw)
+
+
+def test_patched_model_adopts_the_reference_sequence_parallel_state():
+    """A reference trainer initialises the REFERENCE's `parallel_states` (train_prfl.py:119), not this package's; the patched
+    blocks read this package's.  install() / the patched block 0 mirror the reference's state (flag, group, sizes, ranks), follow
+    it when it changes, and leave a natively initialised state (class-swap route) alone."""
+    import importlib
+    from prfl_b200 import parallel
+    ref_shim.load()
+    ps = importlib.import_module("diffusers_lite.utils.parallel_states")
+    saved = (ps._SEQUENCE_PARALLEL_STATE, ps.nccl_info.group, ps.nccl_info.sp_size, ps.nccl_info.rank_within_group, ps.nccl_info.group_id,
+             ps.nccl_info.global_rank)
+    try:
+        assert parallel.adopt_reference_state() is False and not parallel.get_sequence_parallel_state()   # both off: nothing to do
+        group = object()                                                    # stands in for the ProcessGroup the reference created
+        ps.set_sequence_parallel_state(True)
+        ps.nccl_info.group, ps.nccl_info.sp_size, ps.nccl_info.rank_within_group = group, 4, 3
+        ps.nccl_info.group_id, ps.nccl_info.global_rank = 1, 7
+        assert parallel.adopt_reference_state() is True
+        n = parallel.nccl_info
+        assert parallel.get_sequence_parallel_state() and n.group is group and (n.sp_size, n.rank_within_group, n.group_id, n.global_rank) == (4, 3, 1, 7)
+        assert (n.ulysses_degree, n.ring_degree, n.ulysses_rank) == (4, 1, 3) and n.ulysses_group is group
+        assert parallel.adopt_reference_state() is False                    # in sync: a no-op
+        ps.set_sequence_parallel_state(False)                               # the mirror follows the reference back
+        assert parallel.adopt_reference_state() is True and not parallel.get_sequence_parallel_state() and parallel.nccl_info.sp_size == 1
+        # a state this package was given directly is not undone by an idle reference module
+        parallel.set_sequence_parallel_state(True)
+        assert parallel.adopt_reference_state() is False and parallel.get_sequence_parallel_state()
+    finally:
+        parallel.set_sequence_parallel_state(False)
+        parallel._adopted[0] = False
+        (ps._SEQUENCE_PARALLEL_STATE, ps.nccl_info.group, ps.nccl_info.sp_size, ps.nccl_info.rank_within_group, ps.nccl_info.group_id,
+         ps.nccl_info.global_rank) = saved
