@@ -49,6 +49,11 @@ def install(ref_model: nn.Module) -> nn.Module:
     for i, blk in enumerate(ref_model.blocks):
         if hasattr(blk, "_prfl_b200_fast"):
             continue
+        if hasattr(blk, "_fsdp_wrapped_module") or hasattr(blk, "_checkpoint_wrapped_module"):
+            # FSDP swaps a wrapped block's parameters for views of its flat parameter on every forward: a shadow holding the
+            # original nn.Parameter objects would read stale storage.  Refuse instead of computing with old weights.
+            raise RuntimeError(f"blocks.{i} is wrapped ({type(blk).__name__}): install() before / instead of the FSDP and "
+                               "activation-checkpoint wrap — sharded training uses prfl_b200.sharding (INTEGRATION.md B')")
         fast = _shadow(blk, cross)
         fast.train(blk.training)
         object.__setattr__(blk, "_prfl_b200_fast", fast)      # not registered as a submodule: no duplicate state-dict keys

@@ -80,3 +80,16 @@ def test_patched_model_adopts_the_reference_sequence_parallel_state():
         parallel._adopted[0] = False
         (ps._SEQUENCE_PARALLEL_STATE, ps.nccl_info.group, ps.nccl_info.sp_size, ps.nccl_info.rank_within_group, ps.nccl_info.group_id,
          ps.nccl_info.global_rank) = saved
+
+
+def test_install_refuses_wrapped_blocks():
+    """Under the reference's FSDP / checkpoint wrap (train_prfl.py:346-362) a block's parameters are replaced on every forward;
+    install() must refuse rather than share stale tensors."""
+    from torch.distributed.algorithms._checkpoint.checkpoint_wrapper import checkpoint_wrapper
+    from prfl_b200.plugin import install
+    M, _ = ref_shim.load()
+    cfg = synth.tiny_cfg("t2v")
+    ref = M.WanModel(**cfg.kwargs())
+    ref.blocks[1] = checkpoint_wrapper(ref.blocks[1])
+    with pytest.raises(RuntimeError, match="wrapped"):
+        install(ref)
