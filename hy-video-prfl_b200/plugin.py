@@ -46,14 +46,15 @@ def _shadow(blk: nn.Module, cross_attn_type: str) -> WanAttentionBlock:
 def install(ref_model: nn.Module) -> nn.Module:
     """Patch every block of a reference WanModel to run on the prfl_b200 kernels.  Idempotent."""
     cross = "t2v_cross_attn" if getattr(ref_model, "model_type", "t2v") == "t2v" else "i2v_cross_attn"
-    for i, blk in enumerate(ref_model.blocks):
-        if hasattr(blk, "_prfl_b200_fast"):
-            continue
+    for i, blk in enumerate(ref_model.blocks):                  # checked up front: either every block is patched or none
         if hasattr(blk, "_fsdp_wrapped_module") or hasattr(blk, "_checkpoint_wrapped_module"):
             # FSDP swaps a wrapped block's parameters for views of its flat parameter on every forward: a shadow holding the
             # original nn.Parameter objects would read stale storage.  Refuse instead of computing with old weights.
             raise RuntimeError(f"blocks.{i} is wrapped ({type(blk).__name__}): install() before / instead of the FSDP and "
                                "activation-checkpoint wrap — sharded training uses prfl_b200.sharding (INTEGRATION.md B')")
+    for i, blk in enumerate(ref_model.blocks):
+        if hasattr(blk, "_prfl_b200_fast"):
+            continue
         fast = _shadow(blk, cross)
         fast.train(blk.training)
         object.__setattr__(blk, "_prfl_b200_fast", fast)      # not registered as a submodule: no duplicate state-dict keys

@@ -93,3 +93,4 @@ def test_install_refuses_wrapped_blocks():
     ref.blocks[1] = checkpoint_wrapper(ref.blocks[1])
     with pytest.raises(RuntimeError, match="wrapped"):
         install(ref)
+    assert not hasattr(ref.blocks[0], "_prfl_b200_fast")              # nothing was patched
