@@ -72,7 +72,10 @@ def traffic_from_profiles(kernel_prefix="attn_fwd_kernel"):
     """DRAM bytes per launch (read + write) of the dominant kernel from the newest committed `ncu --set full` summary
     (profiles/r*_ncu_full*.csv, written by tools/summarize_ncu.py): (bytes, file) or (None, None)."""
     unit = {"byte": 1.0, "kbyte": 1e3, "mbyte": 1e6, "gbyte": 1e9, "tbyte": 1e12}
-    for path in sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_ncu_full*.csv")), key=os.path.getmtime, reverse=True):
+    def age(path):                     # newest round first (file name r<NN>_...), then newest file: a fresh checkout levels the mtimes
+        digits = "".join(ch for ch in os.path.basename(path)[1:3] if ch.isdigit())
+        return (int(digits) if digits else -1, os.path.getmtime(path))
+    for path in sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_ncu_full*.csv")), key=age, reverse=True):
         try:
             import csv
             rows = [r for r in csv.reader(l for l in open(path) if not l.startswith("#"))]
@@ -456,7 +459,10 @@ def run_ours(args):
     heads_local = HEADS // world
     attn_flops = 4.0 * L * L * HD * heads_local                      # algorithmic, per launch
     achieved = attn_flops / (attn_avg * 1e-3) / 1e12 if attn_avg > 0 else 0.0
-    traffic, traffic_src = traffic_from_profiles() if world == 1 else (None, None)
+    try:
+        traffic, traffic_src = traffic_from_profiles() if world == 1 else (None, None)
+    except Exception:                                            # evidence lookup must never cost the measurement
+        traffic, traffic_src = None, None
     parity = {"reward_logit_full_workload": logit}
     line = {
         "metric": "dit_tokens_per_s", "value": L / (per_step * 1e-3), "unit": "tokens/s", "n_gpus": world, "steps": args.steps,

@@ -31,6 +31,8 @@ def test_traffic_comes_from_the_committed_ncu_summary():
     import bench
     traffic, src = bench.traffic_from_profiles()
     assert src is not None and src.startswith("profiles/") and os.path.exists(os.path.join(ROOT, src))
+    rounds = sorted(int(os.path.basename(f)[1:3]) for f in __import__("glob").glob(os.path.join(ROOT, "profiles", "r*_ncu_full*.csv")))
+    assert int(os.path.basename(src)[1:3]) == rounds[-1]                  # the latest round's capture, whatever the files' mtimes
     algorithmic = 4.0 * 32760 * 40 * 128 * 2                              # Q, K, V, O once each
     assert algorithmic <= traffic <= 1.5 * algorithmic
 
