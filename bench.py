@@ -61,10 +61,13 @@ def bench_config(world):
 
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
-    if os.path.exists(p):
-        d = json.load(open(p))
-        return dict(hbm=d.get("hbm_gbs", 6650.0), tf_burst=d.get("bf16_tflops", 1590.0),
-                    tf_sust=d.get("bf16_tflops_sustained", 1400.0), src="measured")
+    try:
+        if os.path.exists(p):
+            d = json.load(open(p))
+            return dict(hbm=float(d.get("hbm_gbs", 6650.0)), tf_burst=float(d.get("bf16_tflops", 1590.0)),
+                        tf_sust=float(d.get("bf16_tflops_sustained", 1400.0)), src="measured")
+    except Exception:                                            # unreadable file: the profiling recipe's stated fallback
+        pass
     return dict(hbm=6650.0, tf_burst=1590.0, tf_sust=1400.0, src="fallback")
 
 
@@ -110,6 +113,12 @@ class ClockSampler:
             self.rows.append((time.time(), [c.strip() for c in line.split(",")]))
 
     def stop(self, t0, t1):
+        try:
+            return self._stop(t0, t1)
+        except Exception as e:                                   # an unparsable field ("[N/A]") must not cost the measurement
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [f"clock sampling failed: {type(e).__name__}: {e}"]}
+
+    def _stop(self, t0, t1):
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.15)
@@ -117,10 +126,16 @@ class ClockSampler:
         rows = [r for (ts, r) in self.rows if t0 <= ts <= t1 + 0.2 and len(r) >= 7] or [r for (_, r) in self.rows if len(r) >= 7]
         if not rows:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
-        sm = sorted(float(r[0]) for r in rows)
+        def num(v):
+            try:
+                return float(v)
+            except ValueError:                                   # "[N/A]" on boards that do not report the field
+                return None
+        sm = sorted(x for x in (num(r[0]) for r in rows) if x is not None)
+        power = [x for x in (num(r[2]) for r in rows) if x is not None]
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         reasons = [n for i, n in enumerate(names) if any(r[3 + i].lower().startswith("active") for r in rows)]
-        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(rows[0][1]), "power_w_max": max(float(r[2]) for r in rows),
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": num(rows[0][1]), "power_w_max": max(power) if power else None,
                 "samples": len(rows), "reasons": reasons}
 
 
