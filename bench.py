@@ -272,8 +272,8 @@ def gpu_eager_baseline(sd_dev, qa_dev, mlp_dev, x_dev, t_dev, ctx_dev, L, ours_m
 # started, AGREE on the outcome over their own group, and can run the leg again in a more conservative mode.
 CHILD_MODES = [
     ("default: peer-store Ulysses exchange, gradient reduce-scatter overlapped on a side stream", {}),
-    ("conservative: NCCL all-to-all exchange, reduce-scatter on the compute stream",
-     {"PRFL_ULYSSES": "nccl", "PRFL_RS": "serial"}),
+    ("conservative: NCCL all-to-all exchange, reduce-scatter on the compute stream, NCCL without NVLS multicast",
+     {"PRFL_ULYSSES": "nccl", "PRFL_RS": "serial", "NCCL_NVLS_ENABLE": "0"}),
 ]
 
 
