@@ -166,3 +166,27 @@ def test_off_path_options_are_refused_not_silently_ignored():
     for kw in (dict(causal=True), dict(dropout_p=0.1), dict(window_size=(4, 4)), dict(q_lens=torch.tensor([4]))):
         with pytest.raises(NotImplementedError):
             flash_attention(q, q, q, **kw)
+
+
+def test_operand_cache_follows_parameter_updates():
+    """The bf16 / fused operand copies (what autocast re-casts on every Linear call in the reference) are cached per module and must
+    refresh whenever the parameter changes: in-place updates through the Parameter (torch.optim, load_state_dict) bump its version
+    counter, `.to()` / `.data = ...` change its storage, and `bump_weight_epoch()` covers writers that bypass both (updates
+    through `.data`, e.g. the reference's EMA rule model_utils.py:172-175, and ShardedAdamW's flat-buffer updates)."""
+    from prfl_b200.model import _OperandCache, bump_weight_epoch
+    p = torch.nn.Parameter(torch.ones(4, 4))
+    cache, builds = _OperandCache(), []
+
+    def get():
+        return cache.get("w", [p], lambda: builds.append(1) or p.detach().clone())
+    a = get()
+    assert get() is a and len(builds) == 1                                  # hit
+    with torch.no_grad():
+        p.add_(1.0)                                                         # what torch.optim / load_state_dict do
+    assert torch.equal(get(), torch.full((4, 4), 2.0)) and len(builds) == 2
+    p.data = torch.zeros(4, 4)                                              # .to() / re-pointing: new storage
+    assert torch.equal(get(), torch.zeros(4, 4)) and len(builds) == 3
+    p.data.add_(5.0)                                                        # bypasses the version counter ...
+    assert len(builds) == 3 and torch.equal(get(), torch.zeros(4, 4))       # ... so the copy is stale until told:
+    bump_weight_epoch()
+    assert torch.equal(get(), torch.full((4, 4), 5.0)) and len(builds) == 4
