@@ -22,7 +22,7 @@ from typing import Dict, Optional
 
 import torch
 
-__all__ = ["save_checkpoint", "write_model_dir", "load_model_dir", "load_state_dict", "save_optimizer", "load_optimizer"]
+__all__ = ["save_checkpoint", "write_model_dir", "load_model_dir", "load_state_dict", "update_ema_model", "save_optimizer", "load_optimizer"]
 
 MAX_SHARD_BYTES = 5 * 1024 ** 3
 
@@ -120,6 +120,21 @@ def load_state_dict(model_dir: str, postfix: str = ".safetensors") -> Dict[str, 
             chunk = chunk["module"]
         state.update(chunk)
     return state
+
+
+@torch.no_grad()
+def update_ema_model(transformer, ema_transformer, ema_decay: float) -> None:
+    """model_utils.py:172-175: p_ema <- decay * p_ema + (1 - decay) * p for every trainable parameter.  The rule writes through
+    `.data`, which PyTorch's version counters do not see, so the derived GEMM operands of the averaged model are invalidated
+    here.  Resident bf16 weights are refused: increments of (1 - decay) * p fall below one bf16 ulp and would be lost — average
+    the fp32 masters (`ShardedAdamW.full_state_dict()`) instead."""
+    from .model import bump_weight_epoch
+    for p_averaged, p_model in zip(ema_transformer.parameters(), transformer.parameters()):
+        if p_model.requires_grad:
+            if p_averaged.dtype != torch.float32:
+                raise NotImplementedError(f"EMA over {p_averaged.dtype} parameters is lossy; keep the averaged model in fp32")
+            p_averaged.data.mul_(ema_decay).add_(p_model.data.to(p_averaged.dtype), alpha=1 - ema_decay)
+    bump_weight_epoch()
 
 
 def _opt_name(rank: int, world: int) -> str:

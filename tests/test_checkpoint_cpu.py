@@ -162,3 +162,19 @@ def test_save_pretrained_roundtrip_and_reference_loader(tmp_path):
     b = WanModel.from_pretrained(tmp_path / "p")
     sd, back = m.state_dict(), load_state_dict(str(tmp_path / "p"))
     assert all(torch.equal(b.state_dict()[k], sd[k]) and torch.equal(back[k], sd[k]) for k in sd)
+
+
+def test_update_ema_model_rule_and_cache_invalidation():
+    """model_utils.py:172-175 restated: trainable parameters only, p_ema <- d * p_ema + (1 - d) * p; the operand caches of the
+    averaged model are invalidated (the rule writes through `.data`); bf16 averaged parameters are refused."""
+    import pytest
+    from prfl_b200 import model as Mdl
+    from prfl_b200.checkpoint import update_ema_model
+    a, b = torch.nn.Linear(3, 3), torch.nn.Linear(3, 3)
+    a.bias.requires_grad_(False)
+    wa, wb, bb = a.weight.detach().clone(), b.weight.detach().clone(), b.bias.detach().clone()
+    epoch = Mdl._WEIGHT_EPOCH[0]
+    update_ema_model(a, b, 0.9)
+    assert torch.allclose(b.weight, 0.9 * wb + 0.1 * wa) and torch.equal(b.bias, bb) and Mdl._WEIGHT_EPOCH[0] == epoch + 1
+    with pytest.raises(NotImplementedError):
+        update_ema_model(a, torch.nn.Linear(3, 3).bfloat16(), 0.9)
