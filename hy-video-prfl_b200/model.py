@@ -36,6 +36,21 @@ __all__ = ["WanModel", "ModelConfig", "PreparedContext", "WanAttentionBlock", "W
 T5_CONTEXT_TOKEN_NUMBER = 512
 
 
+def no_autocast(fn):
+    """The reference trainers call the model inside `torch.autocast("cuda", dtype=bf16)` (train_prfl.py:669, 723, 748, 960) and
+    keep selected parts in fp32 with nested `amp.autocast(dtype=torch.float32)` blocks (model.py:339-354, 386, 590: time
+    embedding, modulation, head).  Here the precision of every step is explicit (bf16 GEMM / attention operands, fp32
+    accumulation, fp32 residual stream / time embedding / head), so the caller's autocast state must not re-cast the few
+    PyTorch ops on the path: the decorated forward runs with CUDA autocast off, whatever the caller's context."""
+    import functools
+
+    @functools.wraps(fn)
+    def wrapper(*args, **kwargs):
+        with torch.autocast(device_type="cuda", enabled=False):
+            return fn(*args, **kwargs)
+    return wrapper
+
+
 # ------------------------------------------------------------------------------------------------
 # bf16 operand cache: fp32 master parameters -> bf16 copies, refreshed when the parameter changes
 # (what torch.autocast re-does on every Linear call in the reference, SURVEY.md §8a row a17).
@@ -551,6 +566,7 @@ class WanModel(nn.Module):
             ctx = torch.cat([self.img_emb(clip_fea.to(dev)).to(torch.bfloat16), ctx], dim=1)
         return ctx
 
+    @no_autocast
     def forward(self, x, t, context, seq_len, clip_fea=None, y=None, cond_flag=False, output_features=False,
                 selected_layers=[20, 30, 40], gather_features=True):
         """Same contract as the reference (model.py:534-681): x list of [C_in, F, H, W], t [B], context list of

@@ -17,6 +17,7 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from . import ops
+from .model import no_autocast
 
 
 class _SqPool(torch.autograd.Function):
@@ -81,6 +82,7 @@ class QueryAttention(nn.Module):
         self.queries = nn.Parameter(torch.randn(num_queries, feature_dim))
         nn.init.xavier_uniform_(self.queries)
 
+    @no_autocast
     def forward(self, x, e=None, text=None, sp_local: bool = False):
         """x: [B, L, C] or [n_sel, B, L, C] fp32 features (network.py:44-110).
         `sp_local=True` (no-grad scoring under Ulysses sequence parallelism): x holds only THIS rank's token chunk

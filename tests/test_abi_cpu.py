@@ -190,3 +190,23 @@ def test_operand_cache_follows_parameter_updates():
     assert len(builds) == 3 and torch.equal(get(), torch.zeros(4, 4))       # ... so the copy is stale until told:
     bump_weight_epoch()
     assert torch.equal(get(), torch.full((4, 4), 5.0)) and len(builds) == 4
+
+
+def test_forwards_run_with_the_callers_autocast_switched_off():
+    """The trainers call the model under torch.autocast(bf16) (train_prfl.py:669-748); the drop-in's precision is explicit, so
+    its entry points switch CUDA autocast off for their own body (and restore the caller's state afterwards)."""
+    from prfl_b200.model import WanModel, no_autocast
+    from prfl_b200.network import QueryAttention
+    assert hasattr(WanModel.forward, "__wrapped__") and hasattr(QueryAttention.forward, "__wrapped__")
+    seen = []
+
+    @no_autocast
+    def body(v):
+        seen.append(torch.is_autocast_enabled("cuda"))
+        return v + 1
+    assert body(1) == 2 and seen == [False]
+    if torch.cuda.is_available():                                        # only a CUDA box can switch the outer context on
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            body(1)
+            assert torch.is_autocast_enabled("cuda")
+        assert seen == [False, False]
