@@ -47,6 +47,12 @@ MATRIX_ORDER = ("self_attn.q.weight", "self_attn.k.weight", "self_attn.v.weight"
                 "ffn.0.weight", "ffn.2.weight")
 
 
+# Test hook (tests/test_host_logic_emulated_cpu.py): lets the resident layout be built from CPU tensors so that its host logic
+# (views, gradient sink, staging) can run over the emulated kernels.  It opens no CPU path: every kernel wrapper in ops.py
+# still refuses CPU tensors, so with the real library a CPU-resident model fails at its first op.
+_ALLOW_CPU_UNITS = False
+
+
 def _dist_info(group) -> Tuple[int, int]:
     if dist.is_available() and dist.is_initialized():
         return dist.get_world_size(group), dist.get_rank(group)
@@ -80,7 +86,7 @@ class ResidentUnit:
         mats = [(n, named[n]) for n in MATRIX_ORDER if n in named]
         assert mats, "not a WanAttentionBlock"
         dev = mats[0][1].device
-        assert dev.type == "cuda", "resident bf16 units live on the GPU (there is no CPU path)"
+        assert dev.type == "cuda" or _ALLOW_CPU_UNITS, "resident bf16 units live on the GPU (there is no CPU path)"
         self.world, self.rank = world, rank
         self.offsets: Dict[str, Tuple[int, int, torch.Size]] = {}
         o = 0
@@ -265,7 +271,7 @@ class ShardedAdamW:
         except StopIteration:
             raise ValueError("model has no parameters")
         from .model import WanAttentionBlock
-        wan = len(blocks) > 0 and all(isinstance(b, WanAttentionBlock) for b in blocks) and first.is_cuda
+        wan = len(blocks) > 0 and all(isinstance(b, WanAttentionBlock) for b in blocks) and (first.is_cuda or _ALLOW_CPU_UNITS)
         self.resident = wan if resident_bf16 is None else bool(resident_bf16)
         assert not self.resident or wan, "resident_bf16 needs WanAttentionBlock blocks on a CUDA device"
         self.units: List = []

@@ -1,0 +1,300 @@
+"""CPU: the package's HOST logic — model.py / engine.py (hand-written block backward, per-sample loops, checkpointing) /
+network.py / scheduler.py / prfl.py / sampling.py — executed end to end with the C-ABI wrappers replaced by the torch
+stand-ins of tests/ops_emulator.py (what tests/test_kernels_gpu.py holds each kernel to), against the SAME reference goldens
+and oracle the GPU tests use.  What this pins without a GPU: the order and arguments of the kernel calls, in-place / strided
+buffer handling, the backward chain of a block (every gradient the reference produces), ragged batches, the selective
+activation checkpoint, the constant-prompt K/V cache, batched classifier-free guidance, the scheduler's bookkeeping and the
+PRFL chain.  The numerics of the kernels themselves are the GPU tests' business."""
+import pytest
+import torch
+
+import ops_emulator
+from conftest import cos_rel, golden, within_bound_or_eager
+from oracle import synth
+from oracle import unipc_oracle as U
+from oracle import wan_oracle as O
+
+COS, REL = 0.999, 2e-2
+
+
+@pytest.fixture()
+def emu(monkeypatch):
+    from prfl_b200 import model, rope
+    ops = ops_emulator.install(monkeypatch)
+    model.bump_weight_epoch()
+    rope._dev_cache.clear()
+    return ops
+
+
+def _model(cfg, sd, train=False):
+    from prfl_b200.model import WanModel
+    m = WanModel(**cfg.kwargs())
+    m.load_state_dict(sd, strict=True)
+    return m.train() if train else m.eval()
+
+
+def _kw(inp):
+    return dict(t=inp["t"], context=inp["context"], seq_len=inp["seq_len"], clip_fea=inp["clip_fea"], y=inp["y"])
+
+
+@pytest.mark.parametrize("name", ["tiny_t2v", "tiny_i2v"])
+def test_forward_and_gradients_vs_reference_golden(emu, name):
+    fx = golden(name)
+    cfg = O.WanConfig(**fx["cfg"])
+    sd = synth.make_wan_state_dict(cfg, fx["seed_w"])
+    inp = synth.make_inputs(cfg, fx["latent"], fx["seed_in"])
+    m = _model(cfg, sd)
+    with torch.no_grad():
+        out = m(x=inp["x"], **_kw(inp))
+        feats = m(x=inp["x"], **_kw(inp), output_features=True, selected_layers=fx["selected"])
+    assert out[0].dtype == torch.float32 and out[0].shape == fx["out"][0].shape
+    c, r = cos_rel(out[0], fx["out"][0])
+    assert c >= COS and r <= REL, ("noise_pred", c, r)
+    for f, ref in zip(feats, fx["features"]):
+        c, r = cos_rel(f, ref)
+        assert c >= COS and r <= REL, ("features", c, r)
+    assert {"gemm", "attn_fwd", "ln_mod", "rmsnorm_rope_", "patchify", "unpatchify", "ln_mod_split"} <= set(ops_emulator.CALLS)
+    # gradients: the hand-written backward of engine.py behind autograd vs what the real reference produced
+    m.train()
+    x = [u.clone().requires_grad_(True) for u in inp["x"]]
+    out = m(x=x, **_kw(inp))
+    g = torch.Generator().manual_seed(99)
+    cot = [torch.randn(o.shape, generator=g) for o in out]
+    sum((o * c_).sum() for o, c_ in zip(out, cot)).backward()
+    report = {"grad_x": cos_rel(x[0].grad, fx["grad_x"][0])}
+    params = dict(m.named_parameters())
+    for k, ref in fx.items():
+        if k.startswith("grad::"):
+            assert params[k[6:]].grad is not None, k
+            report[k[6:]] = cos_rel(params[k[6:]].grad, ref)
+    # the bf16 stack's own error on this case (the oracle under bf16 autocast rounding) bounds the noise-level gradients
+    sdr = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+    xe = [u.clone().requires_grad_(True) for u in inp["x"]]
+    oe = O.wan_forward(sdr, cfg, xe, inp["t"], inp["context"], inp["seq_len"], inp["clip_fea"], inp["y"], autocast_dtype=torch.bfloat16)
+    sum((o * c_).sum() for o, c_ in zip(oe, cot)).backward()
+    eager = {"grad_x": cos_rel(xe[0].grad, fx["grad_x"][0]), **{k: cos_rel(sdr[k].grad.float(), fx["grad::" + k]) for k in report if k != "grad_x"}}
+    bad = {k: (v, eager[k]) for k, v in report.items() if not within_bound_or_eager(v, eager[k], slack=2.0)}
+    assert not bad, bad
+    assert {"attn_bwd", "ln_mod_bwd", "rmsnorm_rope_bwd_", "gate_bwd", "colsum", "unpatchify_bwd"} <= set(ops_emulator.CALLS)
+
+
+def test_ragged_batch_forward_vs_golden_and_backward_vs_oracle(emu):
+    """B = 2 samples of different sizes, zero-padded to seq_len: forward vs the real reference's output, gradients (the
+    per-sample loop of BlockFn.backward, key-length masking, un-rotated padding rows) vs the fp32 oracle."""
+    fx = golden("tiny_t2v_ragged")
+    cfg = O.WanConfig(**fx["cfg"])
+    sd = synth.make_wan_state_dict(cfg, fx["seed_w"])
+    g = torch.Generator().manual_seed(fx["seed_in"])
+    xs = [torch.randn(16, *lat, generator=g) for lat in fx["latents"]]
+    ctx = [torch.randn(n, cfg.text_dim, generator=g) * 0.08 for n in (40, 17)]
+    t = torch.tensor([400.0, 725.0])
+    m = _model(cfg, sd)
+    with torch.no_grad():
+        out = m(x=xs, t=t, context=ctx, seq_len=fx["seq_len"])
+        feats = m(x=xs, t=t, context=ctx, seq_len=fx["seq_len"], output_features=True, selected_layers=[2])
+    for o, ref in zip(out, fx["out"]):
+        c, r = cos_rel(o, ref)
+        assert o.shape == ref.shape and c >= COS and r <= REL, (c, r)
+    c, r = cos_rel(feats[0], fx["features"][0])
+    assert c >= COS and r <= REL, ("features", c, r)
+    # backward (non-zero head so that gradients reach the blocks)
+    sd = dict(sd)
+    sd["head.head.weight"] = torch.randn(sd["head.head.weight"].shape, generator=g) * 0.02
+    cots = [torch.randn(16, *lat, generator=g) for lat in fx["latents"]]
+    keys = ["blocks.0.self_attn.q.weight", "blocks.1.ffn.0.weight", "blocks.1.cross_attn.v.weight", "blocks.0.modulation",
+            "blocks.1.self_attn.o.bias", "blocks.0.self_attn.norm_k.weight", "patch_embedding.weight"]
+    sdr = {k: v.clone().requires_grad_(k in keys) for k, v in sd.items()}
+    xr = [u.clone().requires_grad_(True) for u in xs]
+    ref = O.wan_forward(sdr, cfg, xr, t, ctx, fx["seq_len"])
+    sum((o * c_).sum() for o, c_ in zip(ref, cots)).backward()
+    mt = _model(cfg, sd, train=True)
+    xg = [u.clone().requires_grad_(True) for u in xs]
+    og = mt(x=xg, t=t, context=ctx, seq_len=fx["seq_len"])
+    sum((o * c_).sum() for o, c_ in zip(og, cots)).backward()
+    params = dict(mt.named_parameters())
+    report = {k: cos_rel(params[k].grad, sdr[k].grad) for k in keys}
+    report.update({f"grad_x{i}": cos_rel(xg[i].grad, xr[i].grad) for i in range(2)})
+    sde = {k: v.clone().requires_grad_(k in keys) for k, v in sd.items()}
+    xe = [u.clone().requires_grad_(True) for u in xs]
+    oe = O.wan_forward(sde, cfg, xe, t, ctx, fx["seq_len"], autocast_dtype=torch.bfloat16)
+    sum((o * c_).sum() for o, c_ in zip(oe, cots)).backward()
+    eager = {k: cos_rel(sde[k].grad.float(), sdr[k].grad) for k in keys}
+    eager.update({f"grad_x{i}": cos_rel(xe[i].grad, xr[i].grad) for i in range(2)})
+    bad = {k: (v, eager[k]) for k, v in report.items() if not within_bound_or_eager(v, eager[k], slack=2.0)}
+    assert not bad, bad
+
+
+def test_selective_checkpoint_equals_full_recompute_bit_for_bit(emu):
+    from prfl_b200 import engine
+    fx = golden("tiny_t2v")
+    cfg = O.WanConfig(**fx["cfg"])
+    sd = synth.make_wan_state_dict(cfg, fx["seed_w"])
+    inp = synth.make_inputs(cfg, fx["latent"], fx["seed_in"])
+    g = torch.Generator().manual_seed(99)
+    grads, counts, prev = {}, {}, engine.SAVE_ATTENTION
+    try:
+        for mode in (True, False):
+            engine.SAVE_ATTENTION = mode
+            m = _model(cfg, sd, train=True)
+            x = [u.clone().requires_grad_(True) for u in inp["x"]]
+            del ops_emulator.CALLS[:]
+            out = m(x=x, **_kw(inp))
+            if mode:
+                cot = [torch.randn(o.shape, generator=g) for o in out]
+            sum((o * c).sum() for o, c in zip(out, cot)).backward()
+            counts[mode] = ops_emulator.CALLS.count("attn_fwd")
+            grads[mode] = {"x": x[0].grad.clone(), **{k: p.grad.clone() for k, p in m.named_parameters() if p.grad is not None}}
+    finally:
+        engine.SAVE_ATTENTION = prev
+    assert set(grads[True]) == set(grads[False]) and all(torch.equal(grads[True][k], grads[False][k]) for k in grads[True])
+    assert counts[False] - counts[True] == cfg.num_layers           # the recompute skipped one self-attention per block
+
+
+def test_reward_chain_vs_reference_golden(emu):
+    from prfl_b200.pavrm import PavrmScorer
+    fx = golden("tiny_reward")
+    cfg = O.WanConfig(**fx["cfg"])
+    sd = synth.make_wan_state_dict(cfg, fx["seed_w"])
+    qa, mlp = synth.make_reward_state_dicts(cfg.dim, fx["seed_w"] + 1)
+    inp = synth.make_inputs(cfg, fx["latent"], fx["seed_in"])
+    scorer = PavrmScorer.from_state_dicts(cfg.kwargs(), sd, qa, mlp, num_blocks=fx["nblocks"], device="cpu")
+    logit, feats = scorer.score(inp["x"], inp["t"], inp["context"], inp["seq_len"], return_features=True)
+    c, r = cos_rel(feats, fx["features"])
+    assert c >= COS and r <= REL and abs(float(logit) - float(fx["logit"])) <= 1e-2, (c, r, float(logit), float(fx["logit"]))
+    scorer.train()
+    f_ref = fx["features"].clone().requires_grad_(True)
+    lg = scorer.mlp(scorer.query_attention(f_ref))
+    prob = torch.sigmoid(lg)
+    loss = torch.nn.functional.binary_cross_entropy(prob, torch.ones_like(prob))
+    assert abs(float(lg.detach()) - float(fx["logit"])) <= 1e-4 and abs(float(loss.detach()) - float(fx["loss"])) <= 1e-4
+    loss.backward()
+    c, r = cos_rel(f_ref.grad, fx["grad_features"])
+    assert c >= 0.99999 and r <= 1e-3, ("grad_features", c, r)
+    x = [u.clone().requires_grad_(True) for u in inp["x"]]
+    fe = scorer.features(x, inp["t"], inp["context"], inp["seq_len"])
+    fe.backward(gradient=fx["grad_features"])
+    c, r = cos_rel(x[0].grad, fx["grad_x"][0])
+    assert c >= COS and r <= REL, ("grad_x", c, r)
+    # frozen blocks (PRFL's reward model): dgrad only — no weight-gradient GEMM, no column reduction is issued
+    for p in scorer.parameters():
+        p.requires_grad_(False)
+    del ops_emulator.CALLS[:]
+    x2 = [u.clone().requires_grad_(True) for u in inp["x"]]
+    scorer.features(x2, inp["t"], inp["context"], inp["seq_len"]).backward(gradient=fx["grad_features"])
+    assert "colsum" not in ops_emulator.CALLS and torch.equal(x2[0].grad, x[0].grad)
+
+
+def test_scheduler_class_reproduces_the_reference_chain(emu):
+    """The real FlowUniPCMultistepScheduler object (bookkeeping of model_outputs / last_sample / orders + folded coefficients)
+    stepping a chain, against the trajectory the unmodified reference scheduler produced (tests/golden/unipc.pt)."""
+    from prfl_b200.scheduler import FlowUniPCMultistepScheduler
+    fx = golden("unipc")
+    g = torch.Generator().manual_seed(fx["seed"])                   # same inputs as tests/golden/make_golden.py::case_unipc
+    x_init = torch.randn(fx["shape"], generator=g)
+    w = torch.randn(fx["shape"], generator=g) * 0.5
+    for (steps, shift, st, order), ch in fx["chains"].items():
+        s = FlowUniPCMultistepScheduler(num_train_timesteps=1000, shift=1, use_dynamic_shifting=False, solver_type=st, solver_order=order)
+        s.set_timesteps(steps, device="cpu", shift=shift)
+        x = x_init.clone()
+        for i, t in enumerate(s.timesteps):
+            x = s.step(U.toy_velocity(x, t, w), t, x, return_dict=False)[0]
+            if torch.isfinite(ch["traj"][i]).all():
+                torch.testing.assert_close(x, ch["traj"][i], rtol=2e-5, atol=2e-5)
+    assert "unipc_step" in ops_emulator.CALLS
+
+
+def test_prepared_context_batched_cfg_and_refl_chain(emu):
+    """Constant-prompt K/V cache == recomputing; cond + uncond as one B = 2 forward == two forwards; the PRFL
+    chain runs m no-grad steps + the differentiable step + the frozen reward model and back-propagates to the VGM only."""
+    from prfl_b200.network import MLP, QueryAttention
+    from prfl_b200.prfl import refl_chain
+    from prfl_b200.sampling import sample_loop
+    from prfl_b200.scheduler import FlowUniPCMultistepScheduler
+    cfg = synth.tiny_cfg("t2v", heads=2, layers=2)
+    sd = synth.make_wan_state_dict(cfg, 5)
+    g = torch.Generator().manual_seed(6)
+    sd["head.head.weight"] = torch.randn(sd["head.head.weight"].shape, generator=g) * 0.02
+    inp = synth.make_inputs(cfg, (2, 8, 8), 7)
+    m = _model(cfg, sd)
+    with torch.no_grad():
+        plain = m(x=inp["x"], **_kw(inp))[0]
+        pc = m.prepare_context(inp["context"])
+        del ops_emulator.CALLS[:]
+        first = m(x=inp["x"], t=inp["t"], context=pc, seq_len=inp["seq_len"])[0]
+        n_first = ops_emulator.CALLS.count("gemm")
+        del ops_emulator.CALLS[:]
+        again = m(x=inp["x"], t=inp["t"], context=pc, seq_len=inp["seq_len"])[0]
+        n_again = ops_emulator.CALLS.count("gemm")
+    assert torch.equal(plain, first) and torch.equal(plain, again) and n_first - n_again == cfg.num_layers   # one K/V GEMM per block saved
+    ctx_null = [torch.randn(9, cfg.text_dim, generator=g) * 0.08]
+    noise = torch.randn(16, 2, 8, 8, generator=g)
+    a = sample_loop(m, noise, inp["context"], ctx_null, inp["seq_len"], sampling_steps=3, batch_cfg=True)[0]
+    b = sample_loop(m, noise, inp["context"], ctx_null, inp["seq_len"], sampling_steps=3, batch_cfg=False, cache_context=False)[0]
+    # bit-identical on the GPU (tests/test_scheduler_gpu.py: per-sample kernels see the same operands); here the fp32 CPU BLAS
+    # behind the emulation rounds a 2-row and a 1-row product differently, and three bf16 steps amplify that last bit
+    c, r = cos_rel(a, b)
+    assert torch.isfinite(a).all() and c >= 0.99999 and r <= 1e-2, (c, r)
+    # PRFL chain: VGM trainable, reward model frozen
+    vgm = _model(cfg, sd, train=True)
+    lrm = _model(cfg, synth.make_wan_state_dict(cfg, 8))
+    lrm.head = None
+    qa, mlp = QueryAttention(cfg.dim, 1, 2, dropout=0.0, return_type="query").eval(), MLP(cfg.dim).eval()
+    for mod in (lrm, qa, mlp):
+        for p in mod.parameters():
+            p.requires_grad_(False)
+    sched = FlowUniPCMultistepScheduler(num_train_timesteps=1000, shift=1, use_dynamic_shifting=False)
+    loss, reward = refl_chain(vgm, lrm, qa, mlp, sched, noise[None], torch.stack(inp["context"]), inp["seq_len"], 2, flow_shift=5.0,
+                              feature_layer=[2], inference_steps=8)
+    loss.backward()
+    assert reward.shape == (1, 1, 1) and torch.isfinite(loss)
+    got = [n for n, p in vgm.named_parameters() if p.grad is not None and float(p.grad.abs().max()) > 0]
+    assert "blocks.0.self_attn.q.weight" in got and "head.head.weight" in got and "patch_embedding.weight" in got
+    assert all(p.grad is None for p in lrm.parameters())
+
+
+@pytest.mark.parametrize("case", ["two_backwards", "ragged_batch"])
+def test_resident_layout_and_gradient_sink_equal_the_autograd_path(emu, monkeypatch, case):
+    """sharding.ResidentUnit / _BlockSink over the emulated kernels (the CUDA-only guard lifted by the test hook): parameters
+    become views of one flat bf16 buffer and the fused operands views of the same bytes; the forward equals the fp32-parameter
+    model's bit for bit; weight gradients written through the sink (one fused [3C, C] / [2C, C] wgrad, `beta` accumulation over
+    a second backward() or over the second sample of a ragged batch) equal the autograd-returned ones bit for bit.  The
+    ragged case is the CPU twin of tests/test_sharding_gpu.py::test_ragged_batch_backward_sink_equals_autograd_and_oracle."""
+    from prfl_b200 import sharding
+    from prfl_b200.sharding import ShardedAdamW
+    monkeypatch.setattr(sharding, "_ALLOW_CPU_UNITS", True)
+    g = torch.Generator().manual_seed(5)
+    if case == "ragged_batch":
+        fx = golden("tiny_t2v_ragged")
+        cfg = O.WanConfig(**fx["cfg"])
+        xs = [torch.randn(16, *lat, generator=g) for lat in fx["latents"]]
+        kw = dict(t=torch.tensor([400.0, 725.0]), context=[torch.randn(n, cfg.text_dim, generator=g) * 0.08 for n in (40, 17)], seq_len=fx["seq_len"])
+    else:
+        cfg = synth.tiny_cfg("i2v", heads=2, layers=2)
+        inp = synth.make_inputs(cfg, (3, 8, 12), 62)
+        xs, kw = inp["x"], _kw(inp)
+    sd = synth.make_wan_state_dict(cfg, 60)
+    sd["head.head.weight"] = torch.randn(sd["head.head.weight"].shape, generator=g) * 0.02
+    a, b = _model(cfg, sd, train=True), _model(cfg, sd, train=True)
+    opt = ShardedAdamW(a, lr=1e-3).attach_hooks()
+    assert opt.resident and a.blocks[0].self_attn.q.weight.dtype == torch.bfloat16
+    wqkv, _ = a.blocks[0].self_attn._qkv_operands()
+    assert wqkv.data_ptr() == a.blocks[0].self_attn.q.weight.data_ptr() and wqkv.shape == (3 * cfg.dim, cfg.dim)
+    with torch.no_grad():
+        assert all(torch.equal(u, v) for u, v in zip(a(x=xs, **kw), b(x=xs, **kw)))
+    for micro in range(2 if case == "two_backwards" else 1):
+        cots = [torch.randn(16, *u.shape[1:], generator=g) for u in xs]
+        sum((o * c).sum() for o, c in zip(a(x=xs, **kw), cots)).backward()
+        sum((o * c).sum() for o, c in zip(b(x=xs, **kw), cots)).backward()
+    shards = opt.reduce_gradients()
+    names = dict(b.named_parameters())
+    checked = 0
+    for ui, u in enumerate(opt.units):
+        for n, (o, cnt, shp) in u.offsets.items():
+            full = (u.sink.prefix + n) if u.kind == "resident" else n
+            want, got = names[full].grad, shards[ui][o:o + cnt].view(shp)
+            if want is None:
+                assert float(got.abs().max()) == 0.0, full
+            else:
+                assert torch.equal(got, want.float()), full
+                checked += 1
+    assert checked > 40 and all(p.grad is None for p in a.parameters())
