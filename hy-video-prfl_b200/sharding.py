@@ -549,6 +549,8 @@ class ShardedAdamW:
                 v.mul_(b2).addcmul_(g, g, value=1 - b2)
                 denom = (v.sqrt() / math.sqrt(1 - b2 ** t)).add_(self.eps)
                 w.addcdiv_(m, denom, value=-self.lr / (1 - b1 ** t))
+                if u.kind == "resident":                            # (test hook _ALLOW_CPU_UNITS) bf16(master), as prfl_adamw_step writes it
+                    u.my_slice(u.wflat).copy_(w)
                 self._publish(u)
             u.has_grad = False
             if u.sink is not None:

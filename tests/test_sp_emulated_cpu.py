@@ -1,0 +1,159 @@
+"""CPU, world_size 2, gloo: the N > 1 HOST logic end to end over the emulated kernels (tests/ops_emulator.py) — the CPU twin of
+tests/sp_check.py, which needs GPUs: Ulysses sequence parallelism through the all-to-all path (token sharding, local-chunk
+patch embedding, RoPE rank offset, head scatter / token gather around attention, feature / head all-gather), the training
+path (sum over SP ranks of the partial gradients == the oracle's SP = 1 gradient), sp-local reward
+pooling == gathered pooling, and the resident layout's gradient sink feeding `ShardedAdamW` with its collectives in stream
+order on one stream (the `PRFL_RS=serial` code path) against dense AdamW on all-reduced gradients."""
+import os
+import sys
+
+import pytest
+import torch
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _worker(rank, world, port, q):
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import warnings
+    warnings.filterwarnings("ignore")
+    import torch.distributed as dist
+    os.environ.update(RANK=str(rank), WORLD_SIZE=str(world), MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    torch.set_num_threads(2)
+    import ops_emulator
+    from conftest import cos_rel
+    from oracle import synth
+    from oracle import wan_oracle as O
+    from prfl_b200 import ops, parallel, sharding
+    from prfl_b200.model import WanModel
+    from prfl_b200.pavrm import PavrmScorer
+    for n in ops_emulator.EMULATED:
+        setattr(ops, n, getattr(ops_emulator, n))
+    sharding._ALLOW_CPU_UNITS = True
+    parallel.initialize_sequence_parallel_state(world)
+    res = {}
+    cfg = synth.tiny_cfg("t2v", heads=4, layers=2, ffn=768)
+    sd = synth.make_wan_state_dict(cfg, 50)
+    g = torch.Generator().manual_seed(7)
+    sd["head.head.weight"] = torch.randn(sd["head.head.weight"].shape, generator=g) * 0.02
+    inp = synth.make_inputs(cfg, (4, 12, 16), 51)                   # 4 x 6 x 8 = 192 tokens
+    kw = dict(t=inp["t"], context=inp["context"], seq_len=inp["seq_len"])
+    sdr = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+    xr = [u.clone().requires_grad_(True) for u in inp["x"]]
+    ref = O.wan_forward(sdr, cfg, xr, inp["t"], inp["context"], inp["seq_len"])
+    cot = [torch.randn(o.shape, generator=torch.Generator().manual_seed(99)) for o in ref]
+    sum((o * c).sum() for o, c in zip(ref, cot)).backward()
+
+    def fresh():
+        m = WanModel(**cfg.kwargs())
+        m.load_state_dict(sd, strict=True)
+        return m.train()
+
+    # ---- training path under SP: forward + sum-over-ranks gradients vs the oracle ----
+    m = fresh()
+    x = [u.clone().requires_grad_(True) for u in inp["x"]]
+    out = m(x=x, **kw)
+    res["fwd"] = cos_rel(out[0].detach(), ref[0].detach())
+    sum((o * c).sum() for o, c in zip(out, cot)).backward()
+    worst = [1.0, 0.0]
+    gx = x[0].grad.clone()
+    dist.all_reduce(gx)
+    grads = {"grad_x": (gx, xr[0].grad)}
+    params = dict(m.named_parameters())
+    for k in ("blocks.0.self_attn.q.weight", "blocks.1.ffn.0.weight", "blocks.0.modulation", "blocks.1.cross_attn.v.weight",
+              "blocks.0.self_attn.norm_k.weight", "blocks.1.self_attn.o.bias", "patch_embedding.weight", "head.head.weight"):
+        gp = params[k].grad.clone()
+        dist.all_reduce(gp)
+        grads[k] = (gp, sdr[k].grad)
+    res["bwd"] = {k: cos_rel(a, b) for k, (a, b) in grads.items()}
+    res["p2p_disabled"] = bool(parallel._p2p_disabled)            # no symmetric memory on CPU: agreed fall-back to the all-to-all path
+    # ---- no-grad: gathered features, sp-local pooling == gathered pooling, vs the oracle ----
+    m.eval()
+    with torch.no_grad():
+        feats = m(x=inp["x"], **kw, output_features=True, selected_layers=[2])
+        rf = O.wan_forward(sd, cfg, inp["x"], inp["t"], inp["context"], inp["seq_len"], output_features=True, selected_layers=[2])
+    res["features"] = cos_rel(feats[0], rf[0]) + (tuple(feats[0].shape) == tuple(rf[0].shape),)
+    qa_sd, mlp_sd = synth.make_reward_state_dicts(cfg.dim, 52)
+    scorer = PavrmScorer.from_state_dicts(cfg.kwargs(), sd, qa_sd, mlp_sd, num_blocks=2, device="cpu")
+    a_ = (inp["x"], inp["t"], inp["context"], inp["seq_len"])
+    logit_sp = float(scorer.score(*a_))
+    logit_g = float(scorer.score(*a_, return_features=True)[0])
+    with torch.no_grad():
+        logit_o = float(O.pavrm_reward(sd, cfg, qa_sd, mlp_sd, inp["x"], inp["t"], inp["context"], inp["seq_len"], selected_layers=(2,), num_blocks=2)[0])
+    res["logits"] = (logit_sp, logit_g, logit_o)
+    # ---- resident layout + gradient sink + ShardedAdamW (collectives in stream order) vs dense AdamW ----
+    from prfl_b200.sharding import ShardedAdamW
+    a, b = fresh(), fresh()
+    opt_a = ShardedAdamW(a, lr=1e-3, weight_decay=0.01).attach_hooks()
+    assert opt_a.resident and opt_a._comm is None
+    opt_b = torch.optim.AdamW(b.parameters(), lr=1e-3, weight_decay=0.01)
+    names_b = dict(b.named_parameters())
+    worst_g = worst_m = 0.0
+    for step in range(2):
+        gi = torch.Generator().manual_seed(200 + step)
+        xin = [torch.randn(inp["x"][0].shape, generator=gi)]
+        cot2 = torch.randn(ref[0].shape, generator=gi)
+        (a(x=xin, **kw)[0] * cot2).sum().backward()
+        (b(x=xin, **kw)[0] * cot2).sum().backward()
+        shards = opt_a.reduce_gradients()
+        for ui, u in enumerate(opt_a.units):
+            full = torch.empty(u.shard * world, dtype=torch.float32)
+            dist.all_gather_into_tensor(full, shards[ui].contiguous())
+            for n, (o, cnt, shp) in u.offsets.items():
+                p_b = names_b[(u.sink.prefix + n) if u.kind == "resident" else n]
+                if p_b.grad is None:
+                    p_b.grad = torch.zeros_like(p_b)
+                dist.all_reduce(p_b.grad)
+                p_b.grad.div_(world)
+                got = full[o:o + cnt].view(shp)
+                worst_g = max(worst_g, float((got - p_b.grad).abs().max() / (p_b.grad.abs().max() + 1e-30)))
+                p_b.grad.copy_(got)
+        na = opt_a.step(max_norm=1.0)
+        nb = torch.nn.utils.clip_grad_norm_(b.parameters(), 1.0)
+        opt_b.step()
+        opt_b.zero_grad(set_to_none=True)
+        assert abs(float(na) - float(nb)) <= 1e-5 * float(nb), (float(na), float(nb))
+        full_sd = opt_a.full_state_dict(to_cpu=True)
+        for k, v in b.state_dict().items():
+            worst_m = max(worst_m, float((full_sd[k].float() - v.detach().float()).abs().max() / (v.detach().float().abs().max() + 1e-12)))
+        b.load_state_dict(full_sd, strict=True)
+    with torch.no_grad():
+        oa, ob = a(x=xin, **kw)[0], b(x=xin, **kw)[0]
+    u0 = opt_a.units[0]
+    res["adamw"] = (worst_g, worst_m, cos_rel(oa, ob), bool(torch.equal(u0.my_slice(u0.wflat).float(), u0.master.bfloat16().float())))
+    q.put((rank, res))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_sequence_parallel_host_logic_world2():
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    import socket
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    got = dict(q.get(timeout=600) for _ in range(world))
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    for rank, res in got.items():
+        assert res["p2p_disabled"] is True
+        c, r = res["fwd"]
+        assert c >= 0.999 and r <= 2e-2, (rank, "fwd", c, r)
+        for k, (c, r) in res["bwd"].items():
+            assert c >= 0.999 and r <= 2e-2, (rank, k, c, r)
+        c, r, same_shape = res["features"]
+        assert same_shape and c >= 0.999 and r <= 2e-2, (rank, "features", c, r)
+        sp, gathered, oracle = res["logits"]
+        assert abs(sp - gathered) <= 1e-5 and abs(sp - oracle) <= 1e-2, (rank, res["logits"])
+        worst_g, worst_m, (c, r), slice_is_bf16_master = res["adamw"]
+        assert worst_g <= 1e-5 and worst_m <= 2e-6 and c >= 0.99999 and slice_is_bf16_master, (rank, res["adamw"])
+    assert got[0]["logits"] == got[1]["logits"] and got[0]["fwd"] == got[1]["fwd"]        # every rank holds the gathered result
