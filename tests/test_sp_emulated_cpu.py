@@ -3,7 +3,8 @@ tests/sp_check.py, which needs GPUs: Ulysses sequence parallelism through the al
 patch embedding, RoPE rank offset, head scatter / token gather around attention, feature / head all-gather), the training
 path (sum over SP ranks of the partial gradients == the oracle's SP = 1 gradient), sp-local reward
 pooling == gathered pooling, and the resident layout's gradient sink feeding `ShardedAdamW` with its collectives in stream
-order on one stream (the `PRFL_RS=serial` code path) against dense AdamW on all-reduced gradients."""
+order on one stream (the `PRFL_RS=serial` code path) against dense AdamW on all-reduced gradients, and the Ulysses x Ring
+no-grad forward (1 x 2)."""
 import os
 import sys
 
@@ -124,6 +125,15 @@ def _worker(rank, world, port, q):
         oa, ob = a(x=xin, **kw)[0], b(x=xin, **kw)[0]
     u0 = opt_a.units[0]
     res["adamw"] = (worst_g, worst_m, cos_rel(oa, ob), bool(torch.equal(u0.my_slice(u0.wflat).float(), u0.master.bfloat16().float())))
+    # ---- Ulysses x Ring (1 x 2): K / V blocks round the ring, LSE merge; no-grad forward vs the oracle ----
+    parallel.initialize_usp_state(1, 2)
+    try:
+        m.eval()
+        with torch.no_grad():
+            out_u = m(x=inp["x"], **kw)
+        res["usp"] = cos_rel(out_u[0], ref[0].detach())
+    finally:
+        parallel.initialize_sequence_parallel_state(world)
     q.put((rank, res))
     dist.barrier()
     dist.destroy_process_group()
@@ -156,4 +166,6 @@ def test_sequence_parallel_host_logic_world2():
         assert abs(sp - gathered) <= 1e-5 and abs(sp - oracle) <= 1e-2, (rank, res["logits"])
         worst_g, worst_m, (c, r), slice_is_bf16_master = res["adamw"]
         assert worst_g <= 1e-5 and worst_m <= 2e-6 and c >= 0.99999 and slice_is_bf16_master, (rank, res["adamw"])
+        c, r = res["usp"]
+        assert c >= 0.999 and r <= 2e-2, (rank, "usp", c, r)
     assert got[0]["logits"] == got[1]["logits"] and got[0]["fwd"] == got[1]["fwd"]        # every rank holds the gathered result
