@@ -94,3 +94,48 @@ def test_install_refuses_wrapped_blocks():
     with pytest.raises(RuntimeError, match="wrapped"):
         install(ref)
     assert not hasattr(ref.blocks[0], "_prfl_b200_fast")              # nothing was patched
+
+
+@pytest.mark.parametrize("mt", ["t2v", "i2v"])
+def test_installed_path_matches_the_reference_forward_and_trains_its_parameters(mt, monkeypatch):
+    """Route B end to end on the REAL reference model (CPU, kernels emulated by tests/ops_emulator.py): the reference's own
+    forward — its patch embedding, time / text / CLIP embeddings, autocast blocks, head and unpatchify — drives the patched
+    blocks with exactly the arguments it passes its own; outputs must match the unpatched reference within north_star's
+    bound, and a backward through the patched model must leave gradients on the reference's own Parameters."""
+    import ops_emulator
+    from conftest import cos_rel
+    from prfl_b200 import model as pm
+    from prfl_b200.plugin import install, uninstall
+    M, _ = ref_shim.load()
+    ops_emulator.install(monkeypatch)
+    pm.bump_weight_epoch()
+    cfg = synth.tiny_cfg(mt)
+    ref = M.WanModel(**cfg.kwargs())
+    sd = synth.make_wan_state_dict(cfg, 3)
+    g = torch.Generator().manual_seed(4)
+    sd["head.head.weight"] = torch.randn(sd["head.head.weight"].shape, generator=g) * 0.02
+    ref.load_state_dict(sd, strict=True)
+    inp = synth.make_inputs(cfg, (3, 8, 12), 5)
+    kw = dict(t=inp["t"], context=inp["context"], seq_len=inp["seq_len"])
+    if mt != "t2v":
+        kw.update(clip_fea=inp["clip_fea"], y=inp["y"])
+    with torch.no_grad():
+        want = ref(inp["x"], **kw)[0]
+        want_f = ref(inp["x"], **kw, output_features=True, selected_layers=[2])[0]
+    install(ref)
+    del ops_emulator.CALLS[:]
+    with torch.no_grad():
+        got = ref(inp["x"], **kw)[0]
+        got_f = ref(inp["x"], **kw, output_features=True, selected_layers=[2])[0]
+    assert ops_emulator.CALLS.count("attn_fwd") >= 2 * 2 * len(ref.blocks)           # the patched blocks did the work
+    for a, b, what in ((got, want, "noise_pred"), (got_f, want_f, "features")):
+        c, r = cos_rel(a, b)
+        assert a.shape == b.shape and c >= 0.999 and r <= 2e-2, (what, c, r)
+    ref.train()
+    x = [u.clone().requires_grad_(True) for u in inp["x"]]
+    ref(x, **kw)[0].square().sum().backward()
+    named = dict(ref.named_parameters())
+    for k in ("blocks.0.self_attn.q.weight", "blocks.1.ffn.2.bias", "blocks.0.modulation", "patch_embedding.weight", "time_projection.1.weight"):
+        assert named[k].grad is not None and float(named[k].grad.abs().max()) > 0, k
+    assert x[0].grad is not None and torch.isfinite(x[0].grad).all()
+    uninstall(ref)
