@@ -298,3 +298,61 @@ def test_resident_layout_and_gradient_sink_equal_the_autograd_path(emu, monkeypa
                 assert torch.equal(got, want.float()), full
                 checked += 1
     assert checked > 40 and all(p.grad is None for p in a.parameters())
+
+
+def test_refl_chain_vs_the_oracle_chain(emu):
+    """prfl.refl_chain (train_prfl.py:631-798: m no-grad denoising steps, the differentiable step, the scheduler step, the frozen
+    reward model, 0.1 * relu(2 - r)) against the same chain built from the two oracles on identical weights and noise: the latent
+    the differentiable step starts from, the reward, the loss, and the VGM gradients (CPU twin of
+    tests/test_scheduler_gpu.py::test_refl_chain_vs_oracle)."""
+    from prfl_b200.network import MLP, QueryAttention
+    from prfl_b200.prfl import refl_chain
+    from prfl_b200.scheduler import FlowUniPCMultistepScheduler
+    cfg = synth.tiny_cfg("t2v", heads=2, layers=2)
+    sd_v, sd_l = synth.make_wan_state_dict(cfg, 80), synth.make_wan_state_dict(cfg, 81)
+    g = torch.Generator().manual_seed(84)
+    sd_v["head.head.weight"] = torch.randn(sd_v["head.head.weight"].shape, generator=g) * 0.02
+    qa_sd, mlp_sd = synth.make_reward_state_dicts(cfg.dim, 82)
+    inp = synth.make_inputs(cfg, (3, 8, 12), 83)
+    noise, steps, mid, shift = inp["x"][0], 8, 2, 5.0
+    # the oracle chain (fp32)
+    sd_vg = {k: v.clone().requires_grad_(True) for k, v in sd_v.items()}
+    osch = U.UniPCOracle()
+    osch.set_timesteps(steps, shift=shift)
+    lat = noise[None].clone()
+    with torch.no_grad():
+        for i in range(mid):
+            t = osch.timesteps[i]
+            lat = osch.step(O.wan_forward(sd_v, cfg, [lat[0]], t[None], inp["context"], inp["seq_len"])[0][None], t, lat)
+    t = osch.timesteps[mid]
+    lat_o = osch.step(O.wan_forward(sd_vg, cfg, [lat[0]], t[None], inp["context"], inp["seq_len"])[0][None], t, lat)
+    logit_o, _ = O.pavrm_reward(sd_l, cfg, qa_sd, mlp_sd, [lat_o[0]], osch.timesteps[mid + 1][None], inp["context"], inp["seq_len"],
+                                selected_layers=(2,), num_blocks=2)
+    reward_o = torch.sigmoid(logit_o.float())
+    loss_o = U.prfl_loss(reward_o)
+    loss_o.backward()
+    # the product chain over the emulated kernels
+    vgm = _model(cfg, sd_v, train=True)
+    lrm = _model(cfg, sd_l)
+    lrm.head = None
+    qa = QueryAttention(cfg.dim, 1, 8, dropout=0.0, return_type="query").eval()
+    qa.load_state_dict(qa_sd, strict=True)
+    mlp = MLP(cfg.dim).eval()
+    mlp.load_state_dict(mlp_sd, strict=True)
+    for mod in (lrm, qa, mlp):
+        for p in mod.parameters():
+            p.requires_grad_(False)
+    sch = FlowUniPCMultistepScheduler(num_train_timesteps=1000, shift=1, use_dynamic_shifting=False)
+    loss, reward = refl_chain(vgm, lrm, qa, mlp, sch, noise[None], torch.stack(inp["context"]), inp["seq_len"], mid,
+                              inference_steps=steps, flow_shift=shift, feature_layer=[2])
+    loss.backward()
+    c, r = cos_rel(sch.last_sample, osch.last_sample)
+    assert c >= COS and r <= REL, ("latent", c, r)
+    assert abs(float(reward.detach()) - float(reward_o.detach())) <= 1e-2 and abs(float(loss.detach()) - float(loss_o.detach())) <= 1e-3
+    if float(loss_o.detach()) > 0:                                  # the hinge is active: gradients flow, compare the large ones
+        params = dict(vgm.named_parameters())
+        big = max(float(v.grad.abs().max()) for v in sd_vg.values() if v.grad is not None)
+        for k in ("head.head.weight", "blocks.1.ffn.2.weight", "blocks.0.self_attn.o.weight"):
+            if float(sd_vg[k].grad.abs().max()) >= 1e-2 * big:
+                c, r = cos_rel(params[k].grad, sd_vg[k].grad)
+                assert c >= 0.99 and r <= 0.15, (k, c, r)          # through the reward MLP's ReLU masks: the GPU test's fixed slack
