@@ -15,7 +15,57 @@ import torch.multiprocessing as mp
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def _worker(rank, world, port, q):
+class FakeP2P:
+    """Stand-in for parallel.P2PUlysses on gloo: the same five entry points with the same BUFFER semantics — every exchange lands
+    in one persistent buffer per kind that the next exchange of that kind overwrites (q/k/v slabs + the dO slab, the output
+    buffer, the fused dQKV buffer) — so that a consumer holding a view past its lifetime reads wrong data here as it would on
+    the GPU.  Transport: all_to_all_single instead of peer stores."""
+
+    def __init__(self, L, H, P, rank):
+        import torch
+        self.P, self.rank, self.L, self.H = P, rank, L, H
+        self.L_loc, self.Hl = L // P, H // P
+        self.qkv = torch.zeros(4, L, self.Hl, 128, dtype=torch.bfloat16)
+        self.o = torch.zeros(self.L_loc, H, 128, dtype=torch.bfloat16)
+        self.dqkv = torch.zeros(self.L_loc, 3 * H * 128, dtype=torch.bfloat16)
+        self.calls = []
+
+    def _scatter(self, t, slab):
+        from prfl_b200.parallel import ulysses_scatter_tokens
+        self.qkv[slab].copy_(ulysses_scatter_tokens(t.contiguous(), self.P))
+        return self.qkv[slab]
+
+    def attention(self, q3, k3, v3, klen):
+        from prfl_b200 import ops
+        self.calls.append("attention")
+        qg, kg, vg = (self._scatter(t, j) for j, t in enumerate((q3, k3, v3)))
+        return self.gather_out(ops.attn_fwd(qg, kg[:klen], vg[:klen]), log=False)
+
+    def scatter_qkv(self, q3, k3, v3):
+        self.calls.append("scatter_qkv")
+        return tuple(self._scatter(t, j) for j, t in enumerate((q3, k3, v3)))
+
+    def gather_out(self, og, log=True):
+        from prfl_b200.parallel import ulysses_gather_tokens
+        if log:
+            self.calls.append("gather_out")
+        self.o.copy_(ulysses_gather_tokens(og.contiguous(), self.P))
+        return self.o
+
+    def scatter_grad(self, do3):
+        self.calls.append("scatter_grad")
+        return self._scatter(do3, 3)
+
+    def gather_grads(self, dqg, dkg, dvg):
+        from prfl_b200.parallel import ulysses_gather_tokens
+        self.calls.append("gather_grads")
+        C = self.H * 128
+        for j, t in enumerate((dqg, dkg, dvg)):
+            self.dqkv[:, j * C:(j + 1) * C].copy_(ulysses_gather_tokens(t.contiguous(), self.P).reshape(self.L_loc, C))
+        return self.dqkv
+
+
+def _worker(rank, world, port, q, fake_p2p=False, full_recompute=False):
     sys.path.insert(0, ROOT)
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     import warnings
@@ -36,6 +86,16 @@ def _worker(rank, world, port, q):
     sharding._ALLOW_CPU_UNITS = True
     parallel.initialize_sequence_parallel_state(world)
     res = {}
+    fakes = {}
+    if full_recompute:                                            # PRFL_CKPT=full: the recompute re-runs the attention kernel
+        from prfl_b200 import engine as _engine
+        _engine.SAVE_ATTENTION = False
+    if fake_p2p:                                                  # the peer-store branches of engine.py over the stand-in above
+        from prfl_b200 import engine
+
+        def get_fake(L, H, device):
+            return fakes.setdefault((L, H), FakeP2P(L, H, world, rank))
+        engine.get_p2p_ulysses = get_fake
     cfg = synth.tiny_cfg("t2v", heads=4, layers=2, ffn=768)
     sd = synth.make_wan_state_dict(cfg, 50)
     g = torch.Generator().manual_seed(7)
@@ -134,12 +194,15 @@ def _worker(rank, world, port, q):
         res["usp"] = cos_rel(out_u[0], ref[0].detach())
     finally:
         parallel.initialize_sequence_parallel_state(world)
+    res["fake_calls"] = [c for f in fakes.values() for c in f.calls]
     q.put((rank, res))
     dist.barrier()
     dist.destroy_process_group()
 
 
-def test_sequence_parallel_host_logic_world2():
+@pytest.mark.parametrize("fake_p2p,full_recompute", [(False, False), (True, False), (True, True)],
+                         ids=["all_to_all_path", "peer_store_branches", "peer_store_branches_full_recompute"])
+def test_sequence_parallel_host_logic_world2(fake_p2p, full_recompute):
     world = 2
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
@@ -147,7 +210,7 @@ def test_sequence_parallel_host_logic_world2():
     with socket.socket() as s:
         s.bind(("127.0.0.1", 0))
         port = s.getsockname()[1]
-    procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
+    procs = [ctx.Process(target=_worker, args=(r, world, port, q, fake_p2p, full_recompute)) for r in range(world)]
     for p in procs:
         p.start()
     got = dict(q.get(timeout=600) for _ in range(world))
@@ -155,7 +218,11 @@ def test_sequence_parallel_host_logic_world2():
         p.join(timeout=120)
         assert p.exitcode == 0
     for rank, res in got.items():
-        assert res["p2p_disabled"] is True
+        if fake_p2p:      # training: 2 blocks x (graph-recording forward + recompute) scatters, 2 x backward exchanges; no-grad: fused form
+            calls = res["fake_calls"]
+            assert calls.count("scatter_qkv") >= 4 and calls.count("gather_grads") >= 2 and calls.count("scatter_grad") >= 2 and "attention" in calls
+        else:
+            assert res["p2p_disabled"] is True
         c, r = res["fwd"]
         assert c >= 0.999 and r <= 2e-2, (rank, "fwd", c, r)
         for k, (c, r) in res["bwd"].items():
