@@ -356,3 +356,34 @@ def test_refl_chain_vs_the_oracle_chain(emu):
             if float(sd_vg[k].grad.abs().max()) >= 1e-2 * big:
                 c, r = cos_rel(params[k].grad, sd_vg[k].grad)
                 assert c >= 0.99 and r <= 0.15, (k, c, r)          # through the reward MLP's ReLU masks: the GPU test's fixed slack
+
+
+def test_i2v_sampling_loop_batched_cfg_and_context_cache(emu):
+    """Image-to-video sampling (image2video.py:357-388): CLIP tokens + conditioning latents ride along; cond + uncond as one B = 2
+    forward with the prompt pair prepared once == two forwards per step without any cache (same values up to CPU BLAS rounding)."""
+    from prfl_b200.sampling import sample_loop
+    cfg = synth.tiny_cfg("i2v", heads=2, layers=2)
+    sd = synth.make_wan_state_dict(cfg, 15)
+    g = torch.Generator().manual_seed(16)
+    sd["head.head.weight"] = torch.randn(sd["head.head.weight"].shape, generator=g) * 0.02
+    inp = synth.make_inputs(cfg, (2, 8, 8), 17)
+    m = _model(cfg, sd)
+    ctx_null = [torch.randn(11, cfg.text_dim, generator=g) * 0.08]
+    noise = torch.randn(16, 2, 8, 8, generator=g)
+    traj = []
+    kw = dict(sampling_steps=4, shift=3.0, guide_scale=4.0, clip_fea=inp["clip_fea"], y=inp["y"])
+    a = sample_loop(m, noise, inp["context"], ctx_null, inp["seq_len"], trajectory=traj, **kw)[0]
+    b = sample_loop(m, noise, inp["context"], ctx_null, inp["seq_len"], batch_cfg=False, cache_context=False, **kw)[0]
+    c_, r_ = cos_rel(a, b)
+    assert a.shape == noise.shape and len(traj) == 4 and torch.isfinite(a).all() and c_ >= 0.99999 and r_ <= 1e-2, (c_, r_)
+    # against the oracle loop: oracle DiT (fp32) + the scheduler oracle, guidance as text2video.py:295-296
+    osch = U.UniPCOracle()
+    osch.set_timesteps(4, shift=3.0)
+    lat = noise[None].clone()
+    with torch.no_grad():
+        for t in osch.timesteps:
+            vc = O.wan_forward(sd, cfg, [lat[0]], t[None], inp["context"], inp["seq_len"], inp["clip_fea"], inp["y"])[0]
+            vu = O.wan_forward(sd, cfg, [lat[0]], t[None], ctx_null, inp["seq_len"], inp["clip_fea"], inp["y"])[0]
+            lat = osch.step((vu + 4.0 * (vc - vu))[None], t, lat)
+    c_, r_ = cos_rel(a, lat[0])
+    assert c_ >= COS and r_ <= REL, ("vs oracle loop", c_, r_)
