@@ -387,3 +387,35 @@ def test_i2v_sampling_loop_batched_cfg_and_context_cache(emu):
             lat = osch.step((vu + 4.0 * (vc - vu))[None], t, lat)
     c_, r_ = cos_rel(a, lat[0])
     assert c_ >= COS and r_ <= REL, ("vs oracle loop", c_, r_)
+
+
+@pytest.mark.skipif(not __import__("oracle.ref_shim", fromlist=["x"]).available(), reason="needs the reference checkout (/root/reference)")
+@pytest.mark.parametrize("shape,with_e", [((1, 150, 256), False), ((2, 1, 150, 256), False), ((2, 1, 150, 256), True), ((3, 256), False)])
+def test_query_attention_equals_the_live_reference_module(emu, shape, with_e):
+    """The algebraic collapse of the single-query pooling (two streaming passes instead of the K/V in-projection GEMM + hd-wide
+    attention) against the UNMODIFIED reference `QueryAttention` (nn.MultiheadAttention inside) on the same weights, for every
+    input rank the reference handles (network.py:58-69), the optional query offset `e`, and `return_type='query'`: values and
+    the gradients w.r.t. features, the learnable query and the in-projection weights."""
+    from oracle import ref_shim
+    from prfl_b200.network import QueryAttention
+    _, N = ref_shim.load()
+    qa_sd, _ = synth.make_reward_state_dicts(256, 91)
+    ref = N.QueryAttention(256, num_queries=1, num_heads=8, dropout=0.0, return_type="query").eval()
+    ours = QueryAttention(256, num_queries=1, num_heads=8, dropout=0.0, return_type="query").eval()
+    ref.load_state_dict(qa_sd, strict=True)
+    ours.load_state_dict(qa_sd, strict=True)
+    g = torch.Generator().manual_seed(92)
+    x = torch.randn(*shape, generator=g)
+    e = torch.randn(1, 256, generator=g) * 0.1 if with_e else None
+    xr, xo = x.clone().requires_grad_(True), x.clone().requires_grad_(True)
+    out_r, out_o = ref(xr, e=e), ours(xo, e=e)
+    assert out_o.shape == out_r.shape
+    torch.testing.assert_close(out_o, out_r, rtol=1e-4, atol=1e-5)
+    cot = torch.randn(out_r.shape, generator=g)
+    (out_r * cot).sum().backward()
+    (out_o * cot).sum().backward()
+    for name, a, b in (("features", xo.grad, xr.grad), ("queries", ours.queries.grad, ref.queries.grad),
+                       ("in_proj_weight", ours.multihead_attn.in_proj_weight.grad, ref.multihead_attn.in_proj_weight.grad),
+                       ("out_proj.weight", ours.multihead_attn.out_proj.weight.grad, ref.multihead_attn.out_proj.weight.grad)):
+        c, r = cos_rel(a, b)
+        assert c >= 0.99999 and r <= 1e-3, (name, c, r)
