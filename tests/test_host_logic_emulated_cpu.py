@@ -419,3 +419,36 @@ def test_query_attention_equals_the_live_reference_module(emu, shape, with_e):
                        ("out_proj.weight", ours.multihead_attn.out_proj.weight.grad, ref.multihead_attn.out_proj.weight.grad)):
         c, r = cos_rel(a, b)
         assert c >= 0.99999 and r <= 1e-3, (name, c, r)
+
+
+@pytest.mark.skipif(not __import__("oracle.ref_shim", fromlist=["x"]).available(), reason="needs the reference checkout (/root/reference)")
+def test_flf2v_model_type_vs_the_live_reference(emu):
+    """`model_type='flf2v'` (first-last-frame-to-video, task flf2v-14b-720p of NAME_MAPPING, train_prfl.py:86-93): two CLIP images
+    per sample go through `MLPProj` with its positional embedding (model.py:392-410) and 514 image tokens precede the text in
+    the cross-attention context.  Product (emulated kernels) vs the unmodified reference model on the same weights."""
+    from oracle import ref_shim
+    from prfl_b200.model import WanModel
+    M, _ = ref_shim.load()
+    kw_model = dict(model_type="flf2v", in_dim=36, dim=256, ffn_dim=512, num_heads=2, num_layers=2, text_dim=64)
+    ref = M.WanModel(**kw_model).eval()
+    g = torch.Generator().manual_seed(21)
+    with torch.no_grad():
+        for p in ref.parameters():
+            p.copy_(torch.randn(p.shape, generator=g) * (0.05 if p.dim() > 1 else 0.02))
+        for n_, p in ref.named_parameters():
+            if n_.endswith("norm_q.weight") or n_.endswith("norm_k.weight") or n_.endswith("norm_k_img.weight") or "norm3.weight" in n_ \
+                    or n_.endswith("proj.0.weight") or n_.endswith("proj.4.weight"):
+                p.add_(1.0)
+    ours = WanModel(**kw_model).eval()
+    assert set(ours.state_dict()) == set(ref.state_dict())
+    ours.load_state_dict(ref.state_dict(), strict=True)
+    x = [torch.randn(16, 2, 8, 8, generator=g)]
+    y = [torch.randn(20, 2, 8, 8, generator=g)]
+    clip = torch.randn(2, 257, 1280, generator=g)                    # first + last frame
+    ctx = [torch.randn(30, 64, generator=g) * 0.5]
+    t = torch.tensor([500.0])
+    with torch.no_grad():
+        want = ref(x, t=t, context=ctx, seq_len=32, clip_fea=clip, y=y)[0]
+        got = ours(x, t=t, context=ctx, seq_len=32, clip_fea=clip, y=y)[0]
+    c, r = cos_rel(got, want)
+    assert got.shape == want.shape and c >= COS and r <= REL, (c, r)
