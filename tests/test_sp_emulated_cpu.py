@@ -3,8 +3,9 @@ tests/sp_check.py, which needs GPUs: Ulysses sequence parallelism through the al
 patch embedding, RoPE rank offset, head scatter / token gather around attention, feature / head all-gather), the training
 path (sum over SP ranks of the partial gradients == the oracle's SP = 1 gradient), sp-local reward
 pooling == gathered pooling, and the resident layout's gradient sink feeding `ShardedAdamW` with its collectives in stream
-order on one stream (the `PRFL_RS=serial` code path) against dense AdamW on all-reduced gradients, and the Ulysses x Ring
-no-grad forward (1 x 2)."""
+order on one stream (the `PRFL_RS=serial` code path) against dense AdamW on all-reduced gradients, two whole PRFL training
+steps (refl_chain, frozen resident reward model, clip + sharded AdamW) against the same steps at SP = 1, and the Ulysses x
+Ring no-grad forward (1 x 2)."""
 import os
 import sys
 
@@ -185,6 +186,69 @@ def _worker(rank, world, port, q, fake_p2p=False, full_recompute=False):
         oa, ob = a(x=xin, **kw)[0], b(x=xin, **kw)[0]
     u0 = opt_a.units[0]
     res["adamw"] = (worst_g, worst_m, cos_rel(oa, ob), bool(torch.equal(u0.my_slice(u0.wflat).float(), u0.master.bfloat16().float())))
+    # ---- two PRFL training steps under SP (resident VGM + gradient sink + ShardedAdamW, frozen resident reward model, refl_chain,
+    #      clip 1.0) against the same two steps at SP = 1 with fp32 parameters and torch.optim.AdamW ----
+    from prfl_b200.network import MLP, QueryAttention
+    from prfl_b200.prfl import refl_chain
+    from prfl_b200.scheduler import FlowUniPCMultistepScheduler
+    from prfl_b200.sharding import make_resident
+    sd_l = synth.make_wan_state_dict(cfg, 81)
+    noise, ctx_b = inp["x"][0], torch.stack(inp["context"])
+
+    def build():
+        vgm = fresh()
+        lrm = WanModel(**cfg.kwargs())
+        lrm.load_state_dict(sd_l, strict=True)
+        lrm.head = None
+        qa = QueryAttention(cfg.dim, 1, 8, dropout=0.0, return_type="query")
+        qa.load_state_dict(qa_sd, strict=True)
+        mlp = MLP(cfg.dim)
+        mlp.load_state_dict(mlp_sd, strict=True)
+        for mod in (lrm, qa, mlp):
+            mod.eval()
+            for p_ in mod.parameters():
+                p_.requires_grad_(False)
+        return vgm, lrm, qa, mlp
+
+    def run(vgm, lrm, qa, mlp, opt_step):
+        losses = []
+        for _ in range(2):
+            sched = FlowUniPCMultistepScheduler(num_train_timesteps=1000, shift=1, use_dynamic_shifting=False)
+            loss, _ = refl_chain(vgm, lrm, qa, mlp, sched, noise[None], ctx_b, inp["seq_len"], 1, inference_steps=6, flow_shift=5.0, feature_layer=[2])
+            loss.backward()
+            opt_step()
+            losses.append(float(loss.detach()))
+        return losses
+
+    vgm, lrm, qa, mlp = build()
+    make_resident(lrm)                                             # frozen reward transformer: bf16 resident, dgrad only
+    opt = ShardedAdamW(vgm, lr=1e-3, weight_decay=0.0).attach_hooks()
+    w_before = {k: v.clone() for k, v in opt.full_state_dict().items()}       # (on CPU tensors `.cpu()` aliases the live parameters)
+    losses_sp = run(vgm, lrm, qa, mlp, lambda: opt.step(max_norm=1.0))
+    w_sp = opt.full_state_dict()
+    sums = torch.tensor([float(u.wflat.float().abs().sum()) for u in opt.units if u.kind == "resident"], dtype=torch.float64)
+    both = [torch.zeros_like(sums) for _ in range(world)]
+    dist.all_gather(both, sums)
+    parallel.initialize_sequence_parallel_state(1)                # the same two steps without SP: every rank computes the whole thing
+    try:
+        vgm1, lrm1, qa1, mlp1 = build()
+        opt1 = torch.optim.AdamW(vgm1.parameters(), lr=1e-3, weight_decay=0.0)
+
+        def step1():
+            for p_ in vgm1.parameters():
+                if p_.grad is not None:
+                    p_.grad.div_(world)                            # FSDP / ShardedAdamW average over ALL ranks, SP peers included
+            torch.nn.utils.clip_grad_norm_(vgm1.parameters(), 1.0)
+            opt1.step()
+            opt1.zero_grad(set_to_none=True)
+        losses_1 = run(vgm1, lrm1, qa1, mlp1, step1)
+    finally:
+        parallel.initialize_sequence_parallel_state(world)
+    w_1 = {k: v.detach().float() for k, v in vgm1.state_dict().items()}
+    upd = {}
+    for k in ("blocks.1.ffn.2.weight", "blocks.0.self_attn.o.weight", "head.head.weight", "blocks.1.modulation"):
+        upd[k] = cos_rel(w_sp[k].float() - w_before[k].float(), w_1[k] - w_before[k].float())
+    res["prfl_steps"] = dict(losses_sp=losses_sp, losses_1=losses_1, upd=upd, replicas_equal=bool(all(torch.equal(b_, both[0]) for b_ in both)))
     # ---- Ulysses x Ring (1 x 2): K / V blocks round the ring, LSE merge; no-grad forward vs the oracle ----
     parallel.initialize_usp_state(1, 2)
     try:
@@ -233,6 +297,13 @@ def test_sequence_parallel_host_logic_world2(fake_p2p, full_recompute):
         assert abs(sp - gathered) <= 1e-5 and abs(sp - oracle) <= 1e-2, (rank, res["logits"])
         worst_g, worst_m, (c, r), slice_is_bf16_master = res["adamw"]
         assert worst_g <= 1e-5 and worst_m <= 2e-6 and c >= 0.99999 and slice_is_bf16_master, (rank, res["adamw"])
+        ps = res["prfl_steps"]
+        assert ps["replicas_equal"], "the resident bf16 weights diverged between ranks"
+        for a_, b_ in zip(ps["losses_sp"], ps["losses_1"]):            # step 2 runs on the weights step 1 produced
+            assert abs(a_ - b_) <= 2e-3, (rank, ps["losses_sp"], ps["losses_1"])
+        assert ps["losses_sp"][1] != ps["losses_sp"][0]
+        for k, (c, r) in ps["upd"].items():                              # Adam's first updates are sign-like: noise-level gradients flip
+            assert c >= 0.8, (rank, k, c, r)
         c, r = res["usp"]
         assert c >= 0.999 and r <= 2e-2, (rank, "usp", c, r)
     assert got[0]["logits"] == got[1]["logits"] and got[0]["fwd"] == got[1]["fwd"]        # every rank holds the gathered result
