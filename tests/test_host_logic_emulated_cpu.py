@@ -452,3 +452,26 @@ def test_flf2v_model_type_vs_the_live_reference(emu):
         got = ours(x, t=t, context=ctx, seq_len=32, clip_fea=clip, y=y)[0]
     c, r = cos_rel(got, want)
     assert got.shape == want.shape and c >= COS and r <= REL, (c, r)
+
+
+def test_edge_inputs_empty_prompt_full_prompt_integer_timestep(emu):
+    """Edge inputs of WanModel.forward against the oracle: a prompt of zero tokens (all 512 context rows are padding,
+    model.py:597-603), a prompt that fills text_len exactly, an int64 timestep (PRFL passes scheduler timesteps, train_prfl.py:671)
+    and a float one give the same result."""
+    cfg = synth.tiny_cfg("t2v", heads=2, layers=2)
+    sd = synth.make_wan_state_dict(cfg, 33)
+    g = torch.Generator().manual_seed(34)
+    sd["head.head.weight"] = torch.randn(sd["head.head.weight"].shape, generator=g) * 0.02
+    x = [torch.randn(16, 2, 8, 12, generator=g)]
+    m = _model(cfg, sd)
+    for n_ctx in (0, 512):
+        ctx = [torch.randn(n_ctx, cfg.text_dim, generator=g) * 0.08]
+        with torch.no_grad():
+            got = m(x=x, t=torch.tensor([731]), context=ctx, seq_len=48)[0]
+            got_f = m(x=x, t=torch.tensor([731.0]), context=ctx, seq_len=48)[0]
+            want = O.wan_forward(sd, cfg, x, torch.tensor([731]), ctx, 48)[0]
+        assert torch.equal(got, got_f)
+        c, r = cos_rel(got, want)
+        assert c >= COS and r <= REL, (n_ctx, c, r)
+    with pytest.raises(AssertionError):                               # a sequence longer than seq_len is the caller's error (model.py:586)
+        m(x=x, t=torch.tensor([731]), context=ctx, seq_len=40)
