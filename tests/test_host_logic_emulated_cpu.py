@@ -475,3 +475,45 @@ def test_edge_inputs_empty_prompt_full_prompt_integer_timestep(emu):
         assert c >= COS and r <= REL, (n_ctx, c, r)
     with pytest.raises(AssertionError):                               # a sequence longer than seq_len is the caller's error (model.py:586)
         m(x=x, t=torch.tensor([731]), context=ctx, seq_len=40)
+
+
+def test_resident_training_state_checkpoint_and_bit_exact_resume(emu, monkeypatch, tmp_path):
+    """Resident bf16 weights + fp32 masters through the reference's checkpoint layout and the optimizer shard file: after two
+    training steps, `save_checkpoint(state_dict=opt.full_state_dict())` + `save_optimizer`; a fresh process-equivalent
+    (`WanModel.from_pretrained` + `ShardedAdamW` + `load_optimizer`) continues bit for bit like the uninterrupted run."""
+    from prfl_b200 import sharding
+    from prfl_b200.checkpoint import load_optimizer, save_checkpoint, save_optimizer
+    from prfl_b200.model import WanModel
+    from prfl_b200.sharding import ShardedAdamW
+    monkeypatch.setattr(sharding, "_ALLOW_CPU_UNITS", True)
+    cfg = synth.tiny_cfg("t2v", heads=2, layers=2)
+    sd = synth.make_wan_state_dict(cfg, 44)
+    g = torch.Generator().manual_seed(45)
+    sd["head.head.weight"] = torch.randn(sd["head.head.weight"].shape, generator=g) * 0.02
+    inp = synth.make_inputs(cfg, (2, 8, 8), 46)
+
+    def steps(m, opt, n, seed):
+        gi = torch.Generator().manual_seed(seed)
+        for _ in range(n):
+            x = [torch.randn(inp["x"][0].shape, generator=gi)]
+            cot = torch.randn(inp["x"][0].shape, generator=gi)
+            (m(x=x, **_kw(inp))[0] * cot).sum().backward()
+            opt.step(max_norm=1.0)
+
+    a = _model(cfg, sd, train=True)
+    oa = ShardedAdamW(a, lr=1e-3, weight_decay=0.01).attach_hooks()
+    steps(a, oa, 2, 1)
+    d = save_checkpoint(a, 0, str(tmp_path), 2, state_dict=oa.full_state_dict())
+    save_optimizer(oa, str(tmp_path), 2)
+    b = WanModel.from_pretrained(d).train()
+    assert b.blocks[0].ffn[0].weight.dtype == torch.float32          # the checkpoint holds the fp32 masters, as the reference's does
+    ob = ShardedAdamW(b, lr=1e-3, weight_decay=0.01).attach_hooks()
+    load_optimizer(ob, d)
+    ua, ub = oa.units[0], ob.units[0]
+    assert torch.equal(ua.master, ub.master) and torch.equal(ua.wflat, ub.wflat) and ua.t == ub.t == 2
+    steps(a, oa, 1, 2)
+    steps(b, ob, 1, 2)
+    fa, fb = oa.full_state_dict(), ob.full_state_dict()
+    assert all(torch.equal(fa[k], fb[k]) for k in fa)
+    with torch.no_grad():
+        assert torch.equal(a(x=inp["x"], **_kw(inp))[0], b(x=inp["x"], **_kw(inp))[0])
