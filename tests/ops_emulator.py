@@ -35,6 +35,8 @@ def ln_mod(x, shift=None, scale=None, gamma=None, beta=None, eps=1e-6, round_bf1
     _log("ln_mod")
     assert x.dtype == f32 and x.is_contiguous()
     C = x.shape[-1]
+    assert C % 256 == 0 and _al16(x, shift, scale, gamma, beta) and (shift is None) == (scale is None) and (gamma is None) == (beta is None)
+    assert all(t is None or (t.dtype == f32 and t.numel() == C and t.is_contiguous()) for t in (shift, scale, gamma, beta))
     xh, mean, rstd = _ln(x.reshape(-1, C), eps)
     y = xh
     if gamma is not None:
@@ -73,6 +75,8 @@ def _rope(t, cos, sin, n_rot, pos0, inverse=False):
 def rmsnorm_rope_(x, w, cos, sin, eps, n_rot=0, pos0=0, out=None, save_rstd=False):
     _log("rmsnorm_rope_")
     assert x.dtype == bf16 and w.dtype == f32 and x.dim() == 2 and x.stride(1) == 1
+    assert x.shape[1] % 256 == 0 and x.stride(0) % 8 == 0 and _al16(x, w, out, cos, sin), (x.shape, x.stride())
+    assert cos is None or (cos.shape[-1] == 64 and pos0 + min(int(n_rot), x.shape[0]) <= cos.shape[0])
     xf = x.float()
     rstd = torch.rsqrt(xf.pow(2).mean(-1) + eps)
     t = (xf * rstd[:, None]).bfloat16().float() * w           # model.py:119: the bf16 rounding sits before the weight
@@ -101,9 +105,23 @@ def _gelu_tanh_grad(x):
     return 0.5 * (1 + t) + 0.5 * x * (1 - t * t) * k * (1 + 3 * 0.044715 * x * x)
 
 
+def _al16(*ts):
+    return all(t is None or t.data_ptr() % 16 == 0 for t in ts)
+
+
 def gemm(a, b, *, a_trans=False, b_trans=False, bias=None, epi=EPI_BF16, out=None, gate=None, aux=None, beta=False, resid=None):
     _log("gemm")
     assert a.dtype == bf16 and b.dtype == bf16 and a.dim() == 2 and b.dim() == 2
+    # the argument contract of prfl_gemm_bf16 (csrc/gemm.cu:376-386): a host path that violates it fails on the GPU with PRFL_E_*
+    M, K = (a.shape[1], a.shape[0]) if a_trans else a.shape
+    N = b.shape[1] if b_trans else b.shape[0]
+    assert M > 0 and N > 0 and K > 0 and N % 8 == 0, (M, N, K)
+    assert K % 8 == 0 or (a_trans and b_trans), f"K={K} must be a multiple of 8 unless both operands are transposed"
+    assert not (a_trans and M % 8), f"transposed A needs M%8==0 (M={M})"
+    assert a.stride(1) == 1 and b.stride(1) == 1 and a.stride(0) % 8 == 0 and b.stride(0) % 8 == 0, (a.stride(), b.stride())
+    assert _al16(a, b, out, bias, gate, aux, resid), "operands must be 16-byte aligned"
+    assert out is None or (out.stride(1) == 1 and out.stride(0) % 4 == 0), out.stride()
+    assert aux is None or (aux.stride(1) == 1 and aux.stride(0) % 8 == 0 and aux.shape == (M, N)), aux.stride()
     A = a.float().t() if a_trans else a.float()
     B = b.float() if b_trans else b.float().t()
     acc = A @ B
@@ -147,7 +165,8 @@ def attn_fwd(q, k, v, scale=None, out=None, need_lse=False):
     _log("attn_fwd")
     for t in (q, k, v):
         assert t.dtype == bf16 and t.dim() == 3 and t.shape[2] == 128 and t.stride(2) == 1
-    assert k.shape == v.shape and k.shape[1] == q.shape[1] and k.shape[0] > 0
+        assert t.stride(0) % 8 == 0 and t.stride(1) % 8 == 0 and _al16(t), (t.stride(), t.data_ptr() % 16)     # csrc/attention_fwd.cu:668-671
+    assert k.shape == v.shape and k.shape[1] == q.shape[1] and k.shape[0] > 0 and q.shape[0] > 0 and q.shape[1] > 0
     scale = 1.0 / math.sqrt(128) if scale is None else scale
     o, lse = _attn(q, k, v, scale)
     if out is None:
@@ -159,7 +178,10 @@ def attn_fwd(q, k, v, scale=None, out=None, need_lse=False):
 def attn_bwd(q, k, v, o, dout, lse, dq=None, dk=None, dv=None, scale=None):
     _log("attn_bwd")
     scale = 1.0 / math.sqrt(128) if scale is None else scale
-    assert lse.shape == (q.shape[1], q.shape[0])
+    assert lse.shape == (q.shape[1], q.shape[0]) and lse.is_contiguous()
+    for t in (q, k, v, o, dout, dq, dk, dv):                         # csrc/attention_bwd.cu:412-418
+        assert t is None or (t.dtype == bf16 and t.stride(2) == 1 and t.stride(0) % 8 == 0 and t.stride(1) % 8 == 0 and _al16(t)), t.stride()
+    assert q.shape[0] > 0 and k.shape[0] > 0
     with torch.enable_grad():
         qf, kf, vf = (t.detach().float().requires_grad_(True) for t in (q, k, v))
         ref, _ = _attn(qf, kf, vf, scale)
