@@ -195,3 +195,39 @@ def test_ragged_batch_backward_sink_equals_autograd_and_oracle():
         eager = {k: cos_rel(sde[k].grad.float().cpu(), sdr[k].grad) for k in keys}
         bad = {k: (v, eager[k]) for k, v in bad.items() if not within_bound_or_eager(v, eager[k])}
     assert not bad, bad
+
+
+@pytest.mark.xfail(strict=False, reason="written after this round's GPU budget was spent: never executed on hardware. It ties the CPU "
+                   "stand-ins of tests/ops_emulator.py (on which the CPU twins of the GPU tests run) to the real kernels; "
+                   "XPASS = the emulation is faithful at model level")
+def test_cpu_emulation_of_the_kernels_matches_the_cuda_path(monkeypatch):
+    """The same tiny model, weights, inputs and cotangent through (a) the CUDA kernels and (b) the torch stand-ins that the
+    CPU suite substitutes for them: outputs and gradients must agree to bf16 rounding (both sides round at the same points).
+    Kept last in the last single-GPU file: the stand-ins are installed with monkeypatch and removed when the test ends."""
+    import ops_emulator
+    from conftest import cos_rel
+    from prfl_b200 import model as pm
+    cfg, sd, inp, make, kw = _models("i2v", 95)
+    g = torch.Generator().manual_seed(96)
+    cot = torch.randn(16, *inp["x"][0].shape[1:], generator=g)
+    a = make()                                                       # CUDA
+    xa = [u.cuda().requires_grad_(True) for u in inp["x"]]
+    oa = a(x=xa, **kw)[0]
+    (oa * cot.cuda()).sum().backward()
+    torch.cuda.synchronize()
+    ops_emulator.install(monkeypatch)                                # from here on prfl_b200.ops.* are the CPU stand-ins
+    pm.bump_weight_epoch()
+    b = pm.WanModel(**cfg.kwargs())
+    b.load_state_dict(sd, strict=True)
+    b.train()
+    xb = [u.clone().requires_grad_(True) for u in inp["x"]]
+    kw_cpu = {k: ([t.cpu() for t in v] if isinstance(v, list) else (v.cpu() if torch.is_tensor(v) else v)) for k, v in kw.items()}
+    ob = b(x=xb, **kw_cpu)[0]
+    (ob * cot).sum().backward()
+    report = {"out": cos_rel(oa.detach().cpu(), ob.detach()), "grad_x": cos_rel(xa[0].grad.cpu(), xb[0].grad)}
+    pa, pb = dict(a.named_parameters()), dict(b.named_parameters())
+    for k in ("blocks.0.self_attn.q.weight", "blocks.1.ffn.0.weight", "blocks.1.cross_attn.k_img.weight", "blocks.0.modulation",
+              "blocks.0.self_attn.norm_k.weight", "patch_embedding.weight", "head.head.weight"):
+        report[k] = cos_rel(pa[k].grad.cpu(), pb[k].grad)
+    bad = {k: v for k, v in report.items() if not (v[0] >= 0.9995 and v[1] <= 2e-2)}
+    assert not bad, bad
