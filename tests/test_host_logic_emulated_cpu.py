@@ -252,7 +252,7 @@ def test_prepared_context_batched_cfg_and_refl_chain(emu):
     assert all(p.grad is None for p in lrm.parameters())
 
 
-@pytest.mark.parametrize("case", ["two_backwards", "ragged_batch"])
+@pytest.mark.parametrize("case", ["two_backwards", "ragged_batch", "two_forwards_one_backward"])
 def test_resident_layout_and_gradient_sink_equal_the_autograd_path(emu, monkeypatch, case):
     """sharding.ResidentUnit / _BlockSink over the emulated kernels (the CUDA-only guard lifted by the test hook): parameters
     become views of one flat bf16 buffer and the fused operands views of the same bytes; the forward equals the fp32-parameter
@@ -281,7 +281,14 @@ def test_resident_layout_and_gradient_sink_equal_the_autograd_path(emu, monkeypa
     assert wqkv.data_ptr() == a.blocks[0].self_attn.q.weight.data_ptr() and wqkv.shape == (3 * cfg.dim, cfg.dim)
     with torch.no_grad():
         assert all(torch.equal(u, v) for u, v in zip(a(x=xs, **kw), b(x=xs, **kw)))
-    for micro in range(2 if case == "two_backwards" else 1):
+    if case == "two_forwards_one_backward":
+        # the Bradley-Terry branch of PAVRM training (train_pavrm.py:816-845): a "win" and a "lose" forward through the same blocks,
+        # ONE backward — every block's backward node runs twice inside it and the second run accumulates onto the first
+        xs2 = [torch.randn(u.shape, generator=g) for u in xs]
+        c1, c2 = ([torch.randn(16, *u.shape[1:], generator=g) for u in xs] for _ in range(2))
+        for mdl in (a, b):
+            (sum((o * c).sum() for o, c in zip(mdl(x=xs, **kw), c1)) - sum((o * c).sum() for o, c in zip(mdl(x=xs2, **kw), c2))).backward()
+    for micro in range({"two_backwards": 2, "ragged_batch": 1}.get(case, 0)):
         cots = [torch.randn(16, *u.shape[1:], generator=g) for u in xs]
         sum((o * c).sum() for o, c in zip(a(x=xs, **kw), cots)).backward()
         sum((o * c).sum() for o, c in zip(b(x=xs, **kw), cots)).backward()
