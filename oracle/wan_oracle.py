@@ -15,7 +15,10 @@ Pinning: `tests/golden/make_golden.py` imports the real reference modules (with 
 build container where /root/reference exists), runs them on seeded weights/inputs and commits
 the outputs under `tests/golden/*.pt`; `tests/test_oracle_golden.py` checks this oracle against
 those fixtures.  The reference ships no tests or golden vectors of its own, so
-parity is pinned by "outputs of the reference itself run here".
+parity is pinned by "outputs of the reference itself run here".  In the build container
+`tests/test_oracle_live_14b_cpu.py` additionally runs the unmodified reference LIVE at the 14B
+dimensions BASELINE.json is quoted on (one block + embeddings + head, forward and backward; the
+reward head at dim 5120) and holds this oracle to the same bounds.
 
 Precision choreography reproduced: fp32 residual stream, RMSNorm over
 the full channel dim with a rounding to the input dtype before the weight multiply, RoPE in
