@@ -67,6 +67,13 @@ HARNESS = textwrap.dedent('''
                      ("prfl_b200.model", mod), ("prfl_b200.network", net), ("prfl_b200.pavrm", pav)]:
         sys.modules[name] = m_
     pkg._lib, pkg.ops, pkg.parallel = lib, ops, par
+    if "--prfl-blocks" in EXTRA:          # success path of the training-step leg: a canned result in place of tools/prfl_step.py
+        ps = types.ModuleType("prfl_step"); ps.LATENT_720P = (21, 90, 160); ps.fit_blocks = lambda w, L: 8
+        def _measure(blocks, m_list, latent, steps=2, i2v=True, opt=True):
+            runs = {"m0": {"s_per_step": 3.5}, "m2": {"s_per_step": 5.0}}
+            return {"blocks": blocks, "runs": runs, "extrapolated_s_per_step": {"per_nograd_forward_s": 0.75, "m0": 3.5, "m19": 17.75, "m38": 32.0}}
+        ps.measure = _measure
+        sys.modules["prfl_step"] = ps
     import bench
     bench.ClockSampler = lambda i: types.SimpleNamespace(stop=lambda a, b: {"sm_mhz": 1.0, "sm_max_mhz": 2.0, "reasons": []})
     sys.argv = ["bench.py", "--steps", "2", "--warmup", "1", "--leg-timeout", %r] + EXTRA
@@ -102,6 +109,17 @@ def test_failing_legs_become_error_entries_and_the_line_is_printed_once():
     assert line["parity"]["same_weights_14b"]["ok"] is False and "error" in line["parity"]["same_weights_14b"]
     assert "unavailable" in line["gpu_baseline"] or "ms_per_step" in line["gpu_baseline"]
     assert "error" in line["prfl_step"]
+
+
+def test_successful_training_step_leg_is_folded_into_the_line():
+    for blocks, expect_published in (("40", True), ("8", False)):
+        res = _run(False, 300, extra=["--prfl-blocks", blocks])
+        assert res.returncode == 0, res.stderr[-3000:]
+        p = _line(res)["prfl_step"]
+        assert p["blocks"] == int(blocks) and p["runs"]["m2"]["s_per_step"] == 5.0 and p["metric"].startswith("PRFL train s/step")
+        assert ("vs_published" in p) is expect_published and ("note" in p) is (not expect_published)
+        if expect_published:
+            assert abs(p["vs_published"]["ratio"] - 43.69 / 17.75) < 1e-9 and "unstated" in p["vs_published"]["caveat"]
 
 
 def test_hanging_leg_trips_the_watchdog_line_still_printed_exit_code_zero():
