@@ -43,6 +43,7 @@ _adopted = [False]            # True while the state above mirrors the reference
 def initialize_sequence_parallel_state(sequence_parallel_size: int):
     """parallel_states.py:34-44."""
     global _SEQUENCE_PARALLEL_STATE
+    _adopted[0] = False                                           # set natively from here on: not a mirror of the reference's module
     if sequence_parallel_size > 1:
         _SEQUENCE_PARALLEL_STATE = True
         initialize_sequence_parallel_group(sequence_parallel_size)
@@ -90,6 +91,7 @@ def initialize_usp_state(ulysses_degree: int, ring_degree: int):
 
 def set_sequence_parallel_state(state: bool):
     global _SEQUENCE_PARALLEL_STATE
+    _adopted[0] = False
     _SEQUENCE_PARALLEL_STATE = state
 
 
