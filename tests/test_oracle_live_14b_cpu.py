@@ -64,8 +64,9 @@ def test_oracle_equals_live_reference_at_14b_dims(mt, monkeypatch):
     from prfl_b200 import model as pm
     ops_emulator.install(monkeypatch)
     pm.bump_weight_epoch()
-    prod = pm.WanModel(**cfg.kwargs())
-    prod.load_state_dict({k: v.detach() for k, v in sd.items()}, strict=True)
+    with torch.device("meta"):                                        # no second random init of 0.6 G parameters: adopt the tensors
+        prod = pm.WanModel(**cfg.kwargs())
+    prod.load_state_dict({k: v.detach().clone() for k, v in sd.items()}, strict=True, assign=True)
     prod.train()
     xp = [u.clone().requires_grad_(True) for u in inp["x"]]
     outp = prod(x=xp, t=inp["t"], context=inp["context"], seq_len=inp["seq_len"], clip_fea=inp["clip_fea"], y=inp["y"])
