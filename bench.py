@@ -21,8 +21,9 @@ reward logit.
              state fits (N = 8), else the largest depth that fits with headroom, stated.  At N > 1 the leg runs in CHILD
              processes with their own process group (`prfl_step_in_children`): a cross-rank hang cannot be cancelled from
              inside a process, so the parents put a deadline on the children, kill exactly those PIDs, agree on the outcome
-             over their own (idle, healthy) group and retry once in a conservative mode (NCCL all-to-all exchange, no
-             side-stream overlap); `prfl_step.attempts` records what happened
+             over their own (idle, healthy) group; after a hang the second and last attempt runs in the bench processes in a
+             conservative mode (NCCL all-to-all exchange, no side-stream overlap) under the leg watchdog, after a crash in the
+             default mode; `prfl_step.attempts` records what happened
   cpu_baseline : the oracle port (torch CPU fp32) timed on this box's host cores on the bounded sample (+ the GPU's
              throughput on that same sample, `gpu_same_sample`, for a like-for-like ratio)
   gpu_baseline : the same oracle port run on THIS GPU with eager PyTorch kernels — bf16 `F.linear` (cuBLAS), flash-attn 2
@@ -608,17 +609,32 @@ def run_ours(args):
             import prfl_step
             Lp = 21 * 45 * 80
             blocks = args.prfl_blocks or prfl_step.fit_blocks(world, Lp)
-            prfl, in_process = None, world == 1
+            prfl, in_process, hung_children = None, world == 1, False
             if world > 1 and not args.prfl_in_process:
                 # the parents stay idle meanwhile; what they still hold (CUDA context, NCCL buffers, the small symmetric exchange
                 # buffers of the scoring step) is a few GB next to the children's <= 135 GB
                 cmd = lambda out: [sys.executable, os.path.join(ROOT, "tools", "prfl_step.py"), "--blocks", str(blocks), "--nograd", "0,2",
                                    "--steps", str(args.prfl_steps), "--out", out]
                 prfl, attempts, in_process = prfl_step_in_children(cmd, world, rank, local, dev, args.prfl_timeout, begin_leg,
-                                                                   tick=lambda: leg.__setitem__(1, time.time()))
+                                                                   tick=lambda: leg.__setitem__(1, time.time()), modes=CHILD_MODES[:1])
+                if prfl is None and not in_process:
+                    # the children hung and were killed (every rank agrees: the flags were all-reduced).  Whether the cause is the
+                    # training step (the one N = 4 hang of round 2) or the child set-up next to the parents' communicators, the second
+                    # and last attempt runs HERE, in the conservative mode — NCCL all-to-all exchange, collectives in stream order —
+                    # under the leg watchdog: it is the last leg, so a hang costs --leg-timeout and nothing that is already measured
+                    hung_children, in_process = True, True
+                    os.environ["PRFL_RS"] = "serial"
+                    parallel._p2p_disabled = True
+                    time.sleep(5.0)                               # the killed children's device memory comes back asynchronously
+                    torch.cuda.empty_cache()
+                    barrier()
             if prfl is None and (in_process or args.prfl_in_process):
                 begin_leg("prfl_step (in process)")
+                t_in = time.time()
                 prfl = prfl_step.measure(blocks, (0, 2), prfl_step.LATENT_720P, steps=args.prfl_steps, i2v=True, opt=True)
+                if attempts is not None:
+                    attempts.append({"mode": ("conservative: NCCL all-to-all exchange, reduce-scatter on the compute stream" if hung_children
+                                              else "default") + ", in the bench processes", "seconds": round(time.time() - t_in, 1), "outcome": "ok"})
             if prfl is None:
                 prfl = {"error": "the training-step leg did not finish in any mode (see attempts); the measurement above is unaffected"}
             if attempts:

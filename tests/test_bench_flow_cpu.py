@@ -75,6 +75,15 @@ HARNESS = textwrap.dedent('''
         ps.measure = _measure
         sys.modules["prfl_step"] = ps
     import bench
+    import os
+    if os.environ.get("HARNESS_HUNG_CHILDREN"):      # the children of the first attempt hung and were killed (agreed by all ranks)
+        bench.prfl_step_in_children = lambda *a, **k: (None, [{"mode": "default", "seconds": 1.0, "outcome": "no result within 1 s: children killed"}], False)
+        par._p2p_disabled = False
+        _m = sys.modules["prfl_step"].measure
+        def _measure_checked(*a, **k):               # the in-process attempt must run in the conservative mode
+            assert os.environ.get("PRFL_RS") == "serial" and par._p2p_disabled is True
+            return _m(*a, **k)
+        sys.modules["prfl_step"].measure = _measure_checked
     bench.ClockSampler = lambda i: types.SimpleNamespace(stop=lambda a, b: {"sm_mhz": 1.0, "sm_max_mhz": 2.0, "reasons": []})
     sys.argv = ["bench.py", "--steps", "2", "--warmup", "1", "--leg-timeout", %r] + EXTRA
     bench.run_ours(bench.build_parser().parse_args())
@@ -227,3 +236,25 @@ def test_two_rank_flow_children_crash_without_a_gpu_then_in_process_fallback_err
     att = line["prfl_step"]["attempts"]
     assert len(att) == 1 and att[0]["outcome"] == "a child exited non-zero" and att[0]["mode"].startswith("default")
     assert "error" in line["prfl_step"]                          # the in-process fallback cannot run on the faked device either
+
+
+def test_two_rank_flow_children_hang_then_conservative_attempt_in_the_bench_processes():
+    """After a hang of the children (killed at the deadline, agreed by both parents) the second and last attempt of the
+    training-step leg runs in the bench processes themselves in the conservative mode (PRFL_RS=serial, NCCL exchange) under the
+    leg watchdog; its result is folded into the line with both attempts recorded."""
+    import socket
+    with socket.socket() as sk:
+        sk.bind(("127.0.0.1", 0))
+        port = sk.getsockname()[1]
+    procs = [_run(False, 300, extra=["--gpus", "2", "--no-parity", "--no-cpu", "--prfl-blocks", "40"], wait=False,
+                  env=dict(RANK=str(r), LOCAL_RANK=str(r), WORLD_SIZE="2", MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), HARNESS_HUNG_CHILDREN="1"))
+             for r in range(2)]
+    outs = [p.communicate(timeout=600) for p in procs]
+    for p, (o, e) in zip(procs, outs):
+        assert p.returncode == 0 and "CLEAN EXIT" in o, (o[-1500:], e[-3000:])
+    line = json.loads([l for l in outs[0][0].splitlines() if l.startswith("{")][0])
+    p = line["prfl_step"]
+    assert "error" not in p and p["blocks"] == 40 and "vs_published" in p
+    att = p["attempts"]
+    assert len(att) == 2 and "children killed" in att[0]["outcome"] and att[1]["outcome"] == "ok"
+    assert att[1]["mode"].startswith("conservative") and att[1]["mode"].endswith("in the bench processes")
