@@ -499,7 +499,7 @@ def run_ours(args):
     }
     emit_lock = threading.Lock()
     emitted = [False]
-    leg = ["(none)", time.time()]
+    leg = ["(none)", time.time(), None]          # name, start, own time limit in seconds (None: --leg-timeout)
 
     def emit(note=None):
         with emit_lock:
@@ -520,14 +520,15 @@ def run_ours(args):
     def watchdog():
         while not emitted[0]:
             time.sleep(1.0)
-            if time.time() - leg[1] > args.leg_timeout:
-                emit(f"leg '{leg[0]}' did not finish within {args.leg_timeout} s; line printed without it and the process ended")
+            limit = leg[2] or args.leg_timeout
+            if time.time() - leg[1] > limit:
+                emit(f"leg '{leg[0]}' did not finish within {limit} s; line printed without it and the process ended")
                 time.sleep(2.0 if rank == 0 else 6.0)
                 os._exit(0)                               # a hung collective cannot be cancelled: leave without the NCCL teardown
     threading.Thread(target=watchdog, daemon=True).start()
 
-    def begin_leg(name):
-        leg[0], leg[1] = name, time.time()
+    def begin_leg(name, limit=None):
+        leg[0], leg[1], leg[2] = name, time.time(), limit
 
     # ---- N > 1: sequence-parallel parity on this very process group (NCCL, symmetric-memory exchange, training path, sharded
     #      optimizer, Ulysses x Ring) — the driver's GPU test box has one GPU, so this is where those numbers become visible ----
@@ -629,7 +630,9 @@ def run_ours(args):
                     torch.cuda.empty_cache()
                     barrier()
             if prfl is None and (in_process or args.prfl_in_process):
-                begin_leg("prfl_step (in process)")
+                # after hung children this attempt gets the children's deadline, not the longer general one: a second hang must
+                # not double the time the bench takes
+                begin_leg("prfl_step (in process)", args.prfl_timeout if hung_children else None)
                 t_in = time.time()
                 prfl = prfl_step.measure(blocks, (0, 2), prfl_step.LATENT_720P, steps=args.prfl_steps, i2v=True, opt=True)
                 if attempts is not None:
