@@ -622,7 +622,7 @@ def run_ours(args):
                     # the children hung and were killed (every rank agrees: the flags were all-reduced).  Whether the cause is the
                     # training step (the one N = 4 hang of round 2) or the child set-up next to the parents' communicators, the second
                     # and last attempt runs HERE, in the conservative mode — NCCL all-to-all exchange, collectives in stream order —
-                    # under the leg watchdog: it is the last leg, so a hang costs --leg-timeout and nothing that is already measured
+                    # under the leg watchdog: it is the last leg, so a second hang costs --prfl-timeout and nothing that is already measured
                     hung_children, in_process = True, True
                     os.environ["PRFL_RS"] = "serial"
                     parallel._p2p_disabled = True
